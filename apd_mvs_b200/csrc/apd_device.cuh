@@ -1,0 +1,274 @@
+// Device-side building blocks of the B200 PatchMatch engine.
+//
+// Numerical contract. The reference is built with `--use_fast_math` (CMakeLists.txt:20) and its
+// outputs are the result of discrete decisions on fp32 costs, so parity needs the SAME rounded
+// operations, not merely the same formulas. This TU is compiled with
+//   -ftz=true -prec-div=false -prec-sqrt=false -fmad=false
+// so the compiler never contracts on its own: every fused multiply-add below is an explicit
+// fmaf() placed where the reference's sm_100 SASS has an FFMA, every plain `*`/`+` is a rounded
+// FMUL/FADD, divisions are written as multiplications by rcpf() (MUFU.RCP) exactly as
+// div.approx is lowered, and sqrtf()/rsqrtf()/__expf()/__sinf()/__cosf() map to the same MUFU ops.
+// Comments of the form "APD.cu:NNN" name the reference lines whose arithmetic is being matched.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/apd_b200.h"
+
+namespace apd {
+
+constexpr int kRefPad = 8;        // replicated border of the pitch-linear reference-image copy
+constexpr int kHalo = 5;          // strong_radius (main.h:83)
+constexpr float kCostMax = 2.0f;
+
+// ---- per-view constants (built once per run by k_setup_views) ---------------------------------
+struct ViewConst {
+	float Rrel[9];      // R_src * R_ref^T            (APD.cu:317-325)
+	float trel[3];      // R_src * (C_ref - C_src)    (APD.cu:326-331)
+	float K0, K2, K4, K5, K8;   // source intrinsics used by the homography (APD.cu:354-362)
+	float wf, hf;       // float(width), float(height) of the source image (APD.cu:546)
+	float baseline;     // |c_ref - c_src| as DepthToWeak/LocalRefine compute it (APD.cu:2037-2042)
+	apd_camera cam;     // full source camera for the geometric-consistency term (APD.cu:752-789)
+};
+
+struct RefConst {
+	apd_camera cam;
+	float rK0, rK4;     // MUFU.RCP(K[0]), MUFU.RCP(K[4])
+	float kk;           // K[0] * rcp(K[4])            (APD.cu:208)
+};
+
+// ---- XORWOW (curand default generator), 24 B of live state ------------------------------------
+// curandState is 48 B (APD.cpp:640); only v[5] and d are ever live on this path because the
+// reference uses curand()/curand_uniform() only (no Box-Muller). Same recurrence as
+// curand_kernel.h: identical streams given identical (v, d).
+struct Rng { uint32_t v0, v1, v2, v3, v4, d; };
+
+__device__ __forceinline__ uint32_t rng_next(Rng &s) {
+	uint32_t t = s.v0 ^ (s.v0 >> 2);
+	s.v0 = s.v1; s.v1 = s.v2; s.v2 = s.v3; s.v3 = s.v4;
+	s.v4 = (s.v4 ^ (s.v4 << 4)) ^ (t ^ (t << 1));
+	s.d += 362437u;
+	return s.v4 + s.d;
+}
+__device__ __forceinline__ float rng_uniform(Rng &s) {
+	// curand_uniform: x * 2^-32 + 2^-33, one FFMA in the reference SASS
+	return fmaf((float)rng_next(s), 2.3283064365386962890625e-10f, 1.16415321826934814453125e-10f);
+}
+__device__ __forceinline__ Rng rng_load(const uint2 *g, size_t idx) {
+	const uint2 *p = g + idx * 3;
+	uint2 a = p[0], b = p[1], c = p[2];
+	Rng s; s.v0 = a.x; s.v1 = a.y; s.v2 = b.x; s.v3 = b.y; s.v4 = c.x; s.d = c.y;
+	return s;
+}
+__device__ __forceinline__ void rng_store(uint2 *g, size_t idx, const Rng &s) {
+	uint2 *p = g + idx * 3;
+	p[0] = make_uint2(s.v0, s.v1); p[1] = make_uint2(s.v2, s.v3); p[2] = make_uint2(s.v4, s.d);
+}
+
+// ---- approximate math, named after the SASS they become --------------------------------------
+__device__ __forceinline__ float rcpf(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrtaf(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrtaf(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// ---- geometry helpers --------------------------------------------------------------------------
+// ComputeDepthfromPlaneHypothesis, APD.cu:206-209
+__device__ __forceinline__ float plane_depth(const RefConst &rc, const float4 pl, const float xf, const float yf) {
+	const float *K = rc.cam.K;
+	float b = pl.y * (rc.kk * (yf - K[5]));
+	float t = fmaf(pl.x, xf - K[2], b);
+	float den = fmaf(K[0], pl.z, t);
+	return (K[0] * -pl.w) * rcpf(den);
+}
+// Get3DPoint, APD.cu:159-164 (X[2] = depth)
+__device__ __forceinline__ void backproject(const RefConst &rc, float xf, float yf, float depth, float &X0, float &X1) {
+	X0 = (depth * (xf - rc.cam.K[2])) * rc.rK0;
+	X1 = (depth * (yf - rc.cam.K[5])) * rc.rK4;
+}
+// GetDistance2Origin, APD.cu:187-192
+__device__ __forceinline__ float plane_offset(const RefConst &rc, float xf, float yf, float depth, float nx, float ny, float nz) {
+	float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
+	float a = X1 * ny;
+	a = fmaf(X0, nx, a);
+	a = fmaf(depth, nz, a);
+	return -a;
+}
+__device__ __forceinline__ void normalize3(float &x, float &y, float &z) {   // NormalizeVec3, APD.cu:126-133
+	float n2 = y * y; n2 = fmaf(x, x, n2); n2 = fmaf(z, z, n2);
+	float r = rsqrtaf(n2);
+	x *= r; y *= r; z *= r;
+}
+// GenerateRandomNormal, APD.cu:211-237
+__device__ __forceinline__ float4 random_normal(const RefConst &rc, float xf, float yf, Rng &rng, float depth) {
+	float q1, q2, s;
+	do {
+		q1 = fmaf(rng_uniform(rng), 2.0f, -1.0f);
+		q2 = fmaf(rng_uniform(rng), 2.0f, -1.0f);
+		s = fmaf(q1, q1, q2 * q2);
+	} while (s >= 1.0f);
+	float sq = sqrtaf(1.0f - s);
+	float nx = sq * (q1 + q1);
+	float ny = sq * (q2 + q2);
+	float nz = 1.0f - (s + s);
+	float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
+	float n2 = X1 * X1; n2 = fmaf(X0, X0, n2); n2 = fmaf(depth, depth, n2);
+	float rn = rcpf(sqrtaf(n2));
+	float vx = X0 * rn, vy = X1 * rn, vz = depth * rn;
+	float dot = ny * vy; dot = fmaf(nx, vx, dot); dot = fmaf(nz, vz, dot);
+	if (dot > 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+	normalize3(nx, ny, nz);
+	return make_float4(nx, ny, nz, 0.0f);
+}
+// GeneratePerturbedNormal, APD.cu:239-274 (perturbation = 0.02f * M_PI folded to a float constant)
+__device__ __forceinline__ float4 perturbed_normal(const RefConst &rc, float xf, float yf, const float4 n, Rng &rng) {
+	const float pert = (float)(0.02f * 3.14159265358979323846);
+	float a1 = (rng_uniform(rng) - 0.5f) * pert;
+	float a2 = (rng_uniform(rng) - 0.5f) * pert;
+	float a3 = (rng_uniform(rng) - 0.5f) * pert;
+	float s1 = __sinf(a1), c1 = __cosf(a1);
+	float s2 = __sinf(a2), c2 = __cosf(a2);
+	float s3 = __sinf(a3), c3 = __cosf(a3);
+	float c1c3 = c1 * c3, s1c3 = s1 * c3, s3c1 = s3 * c1;
+	float R0 = c2 * c3;
+	float R1 = fmaf(s2, s1c3, -s3c1);
+	float R2 = fmaf(s1, s3, s2 * c1c3);
+	float R3 = s3 * c2;
+	float R4 = fmaf(s3, s1 * s2, c1c3);
+	float R5 = fmaf(s3, s2 * c1, -s1c3);
+	float R7 = s1 * c2;
+	float R8 = c1 * c2;
+	float px = fmaf(n.z, R2, fmaf(n.x, R0, n.y * R1));
+	float py = fmaf(n.z, R5, fmaf(n.x, R3, n.y * R4));
+	float pz = fmaf(n.z, R8, fmaf(n.y, R7, -(n.x * s2)));
+	// view direction at depth 1 (APD.cu:241)
+	float X0 = (xf - rc.cam.K[2]) * rc.rK0;
+	float X1 = (yf - rc.cam.K[5]) * rc.rK4;
+	float n2 = fmaf(X0, X0, X1 * X1) + 1.0f;
+	float rn = rcpf(sqrtaf(n2));
+	float vx = X0 * rn, vy = X1 * rn;
+	float dot = vx * px; dot = fmaf(vy, py, dot); dot = fmaf(pz, rn, dot);
+	if (dot >= 0.0f) { px = n.x; py = n.y; pz = n.z; }
+	normalize3(px, py, pz);
+	return make_float4(px, py, pz, 0.0f);
+}
+
+// ---- homography (APD.cu:303-363) with the per-view part hoisted ---------------------------------
+struct Homog { float h[9]; };
+__device__ __forceinline__ Homog make_homography(const RefConst &rc, const ViewConst &vc, const float4 pl) {
+	const float rw = rcpf(pl.w);
+	float H[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		const float t = vc.trel[r];
+		H[3 * r + 0] = fmaf(-(pl.x * t), rw, vc.Rrel[3 * r + 0]);
+		H[3 * r + 1] = fmaf(-(pl.y * t), rw, vc.Rrel[3 * r + 1]);
+		H[3 * r + 2] = fmaf(-(pl.z * t), rw, vc.Rrel[3 * r + 2]);
+	}
+	const float K2 = rc.cam.K[2], K5 = rc.cam.K[5];
+	float T[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		T[3 * r + 0] = H[3 * r + 0] * rc.rK0;
+		T[3 * r + 1] = H[3 * r + 1] * rc.rK4;
+		T[3 * r + 2] = H[3 * r + 2] + fmaf(K2 * -H[3 * r + 0], rc.rK0, -((K5 * H[3 * r + 1]) * rc.rK4));
+	}
+	Homog o;
+	o.h[0] = fmaf(vc.K0, T[0], vc.K2 * T[6]);
+	o.h[1] = fmaf(vc.K0, T[1], vc.K2 * T[7]);
+	o.h[2] = fmaf(vc.K0, T[2], vc.K2 * T[8]);
+	o.h[3] = fmaf(vc.K4, T[3], vc.K5 * T[6]);
+	o.h[4] = fmaf(vc.K4, T[4], vc.K5 * T[7]);
+	o.h[5] = fmaf(vc.K4, T[5], vc.K5 * T[8]);
+	o.h[6] = vc.K8 * T[6];
+	o.h[7] = vc.K8 * T[7];
+	o.h[8] = vc.K8 * T[8];
+	return o;
+}
+// ComputeCorrespondingPoint for the patch centre (APD.cu:365-372 as inlined at APD.cu:545)
+__device__ __forceinline__ bool centre_inside(const Homog &Hm, const ViewConst &vc, float xf, float yf) {
+	const float *h = Hm.h;
+	float z = h[8] + fmaf(xf, h[6], yf * h[7]);
+	float rz = rcpf(z);
+	float x = (h[2] + fmaf(xf, h[0], yf * h[1])) * rz;
+	float y = (h[5] + fmaf(xf, h[3], yf * h[4])) * rz;
+	return !(x >= vc.wf || x < 0.0f || y >= vc.hf || y < 0.0f);
+}
+
+// ---- NCC epilogue (APD.cu:592-610) -----------------------------------------------------------------
+struct NccSums { float r, rr, s, ss, rs; };
+__device__ __forceinline__ float ncc_cost(const NccSums &a, float inv_w) {
+	float mr = inv_w * a.r;
+	float ms = inv_w * a.s;
+	float var_r = fmaf(inv_w, a.rr, -(mr * mr));
+	float var_s = fmaf(inv_w, a.ss, -(ms * ms));
+	const float kMinVar = 1e-5f;
+	if (var_r < kMinVar || var_s < kMinVar) return kCostMax;
+	float covar = fmaf(-mr, ms, inv_w * a.rs);
+	float den = sqrtaf(var_r * var_s);
+	float c = fmaf(-covar, rcpf(den), 1.0f);
+	return fmaxf(0.0f, fminf(kCostMax, c));
+}
+
+// One source tap (APD.cu:570-573): projective warp with the x-part hoisted out of the row loop,
+// exactly as the reference compiles it (FMUL / FFMA / FADD / MUFU.RCP / FFMA +0.5).
+__device__ __forceinline__ float src_tap(cudaTextureObject_t tex, int layer, const float *h, float ax, float ay, float az, float yf) {
+	float xs = h[2] + fmaf(h[1], yf, ax);
+	float ys = h[5] + fmaf(h[4], yf, ay);
+	float zs = h[8] + fmaf(h[7], yf, az);
+	float rz = rcpf(zs);
+	return tex2DLayered<float>(tex, fmaf(xs, rz, 0.5f), fmaf(ys, rz, 0.5f), layer);
+}
+
+// ComputeBilateralNCCOld (APD.cu:530-614) for the pixel at tile-local (lx, ly): 6x6 taps at
+// offsets {-5,-3,-1,1,3,5}^2, x-offset outer / y-offset inner, row sums folded into totals.
+// `tile` points at the shared-memory copy of the reference image, tile[(ly+5+j)*pitch + lx+5+i].
+template <int RADIUS, int INC>
+__device__ __forceinline__ float ncc_strong(cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc,
+                                            const float *tile, int pitch, int lx, int ly, int px, int py, float inv_w) {
+	if (!centre_inside(Hm, vc, (float)px, (float)py)) return kCostMax;
+	const float *h = Hm.h;
+	NccSums t = {0.f, 0.f, 0.f, 0.f, 0.f};
+	const float *base = tile + (ly + kHalo) * pitch + (lx + kHalo);
+#pragma unroll
+	for (int i = -RADIUS; i <= RADIUS; i += INC) {
+		const float xf = (float)(px + i);
+		const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
+		NccSums r = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+		for (int j = -RADIUS; j <= RADIUS; j += INC) {
+			const float rp = base[j * pitch + i];
+			const float sp = src_tap(tex, layer, h, ax, ay, az, (float)(py + j));
+			r.r += rp; r.rr = fmaf(rp, rp, r.rr); r.rs = fmaf(rp, sp, r.rs);
+			r.s += sp; r.ss = fmaf(sp, sp, r.ss);
+		}
+		t.r += r.r; t.rr += r.rr; t.s += r.s; t.ss += r.ss; t.rs += r.rs;
+	}
+	return ncc_cost(t, inv_w);
+}
+
+// ---- kernel arguments -------------------------------------------------------------------------------
+struct Args {
+	int W, H, S;                 // S = number of source views = num_images - 1
+	int half_rows;               // rows reachable by the reference's half launch (APD.cu:2400-2403)
+	int ref_pitch;               // elements per row of ref_pad
+	float depth_min, depth_max;
+	int top_k, state, geom, weak_peak_radius, rotate_time;
+	float geom_factor, ransac_threshold;
+	const float *inv_w;          // [0] = MUFU.RCP(36.0f) strong window, [1] = MUFU.RCP(9.0f) anchor window
+	cudaTextureObject_t img_tex;     // layered: layer v = image v (0 = reference)
+	cudaTextureObject_t depth_tex;   // layered depth maps (geom consistency)
+	const float *ref_pad;        // reference image with kRefPad replicated border
+	const ViewConst *views;      // [S]
+	const RefConst *ref;
+	float4 *planes; float4 *fit_planes; float *costs;
+	uint32_t *sel_views; uint8_t *states; uint2 *rng; uint4 *view_w;
+	short2 *anchors;             // [9][W*H]: slot k of pixel p at anchors[k*W*H + p] (reference: compact [weak_idx*9+k])
+	short2 *nearest; uint8_t *reliable;
+};
+
+// view weights: 32 nibbles (sum <= 15) in one uint4 per pixel (reference: 32 bytes, APD.cpp:645)
+struct VW { unsigned long long lo, hi; };
+__device__ __forceinline__ void vw_add(VW &w, int v) { if (v < 16) w.lo += 1ull << (4 * v); else w.hi += 1ull << (4 * (v - 16)); }
+__device__ __forceinline__ int vw_get(const VW &w, int v) { return (int)(((v < 16) ? (w.lo >> (4 * v)) : (w.hi >> (4 * (v - 16)))) & 15ull); }
+__device__ __forceinline__ VW vw_load(const uint4 *g, size_t i) { uint4 u = g[i]; VW w; w.lo = ((unsigned long long)u.y << 32) | u.x; w.hi = ((unsigned long long)u.w << 32) | u.z; return w; }
+__device__ __forceinline__ void vw_store(uint4 *g, size_t i, const VW &w) { g[i] = make_uint4((uint32_t)w.lo, (uint32_t)(w.lo >> 32), (uint32_t)w.hi, (uint32_t)(w.hi >> 32)); }
+
+}  // namespace apd

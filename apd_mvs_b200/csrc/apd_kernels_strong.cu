@@ -1,0 +1,735 @@
+// sm_100a kernels of the all-pixels / strong-pixel part of the PatchMatch path:
+//   k_setup_views      per-view constants (hoists APD.cu:305-331 out of every NCC call)
+//   k_pad_ref          reference image -> pitch-linear copy with replicated border (TMA/smem source)
+//   k_rng_seed         K1  InitRandomStates           APD.cu:791-804
+//   k_init_planes      K5  RandomInitialization       APD.cu:806-835 (+616-693)
+//   k_strong           K6/K7 Black/RedPixelUpdateStrong APD.cu:1547-1585 -> :982-1321 -> :837-890
+//   k_depth_normal     K11 GetDepthandNormal          APD.cu:1587-1602
+//   k_median           K12/K13 Black/RedPixelFilterStrong APD.cu:1604-1748
+//   k_classify         K14 DepthToWeak                APD.cu:1990-2144
+//   k_local_refine     K15 LocalRefine                APD.cu:2146-2232
+// Design (not a translation): one thread per pixel as in the reference, but
+//   * the reference window lives in shared memory (one tile per block, loaded once, reused by all
+//     14*S NCC evaluations of a pixel) instead of a second texture fetch per tap;
+//   * source views are layers of ONE layered texture (uniform handle, per-view layer index);
+//   * all camera algebra that does not depend on the hypothesis is precomputed per view and read
+//     from shared memory, the 6x6 tap loop is fully unrolled so 36 texture fetches are in flight
+//     per thread, the 8xS cost matrix sits in shared memory (no local-memory stack), the RNG
+//     state is loaded/stored once per kernel (24 B instead of 48 B), views with zero sampling
+//     weight are skipped in the 6 post-selection evaluations (their weight multiplies them by 0);
+//   * no host synchronisation between launches.
+#include <curand_kernel.h>
+#include "apd_device.cuh"
+
+namespace apd {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_setup_views(const apd_camera *cams, int S, ViewConst *vout, RefConst *rout, float *inv_w_out) {
+	const int v = threadIdx.x;
+	const apd_camera rc = cams[0];
+	if (v == 0) {
+		RefConst r; r.cam = rc; r.rK0 = rcpf(rc.K[0]); r.rK4 = rcpf(rc.K[4]); r.kk = rc.K[0] * r.rK4;
+		*rout = r;
+		// 1/sum(weights) of the 6x6 and 3x3 windows: the reference accumulates 36 (9) times 1.0f and
+		// takes MUFU.RCP of the sum at run time (APD.cu:592, :488)
+		float w36 = 0.f, w9 = 0.f;
+		for (int i = 0; i < 36; ++i) w36 += 1.0f;
+		for (int i = 0; i < 9; ++i) w9 += 1.0f;
+		inv_w_out[0] = rcpf(w36); inv_w_out[1] = rcpf(w9);
+	}
+	if (v >= S) return;
+	const apd_camera sc = cams[v + 1];
+	ViewConst o;
+	// -C = R^T t, accumulated as FMUL(middle) / FFMA / FFMA (APD.cu:307-312)
+	float a[3], b[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		a[k] = fmaf(rc.R[6 + k], rc.t[2], fmaf(rc.R[k], rc.t[0], rc.R[3 + k] * rc.t[1]));
+		b[k] = fmaf(sc.R[6 + k], sc.t[2], fmaf(sc.R[k], sc.t[0], sc.R[3 + k] * sc.t[1]));
+	}
+	float C[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) C[k] = b[k] - a[k];   // ref_C - src_C
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+#pragma unroll
+		for (int c = 0; c < 3; ++c)
+			o.Rrel[3 * r + c] = fmaf(sc.R[3 * r + 2], rc.R[3 * c + 2], fmaf(sc.R[3 * r + 0], rc.R[3 * c + 0], sc.R[3 * r + 1] * rc.R[3 * c + 1]));
+		o.trel[r] = fmaf(sc.R[3 * r + 2], C[2], fmaf(sc.R[3 * r + 0], C[0], sc.R[3 * r + 1] * C[1]));
+	}
+	o.K0 = sc.K[0]; o.K2 = sc.K[2]; o.K4 = sc.K[4]; o.K5 = sc.K[5]; o.K8 = sc.K[8];
+	o.wf = (float)sc.width; o.hf = (float)sc.height;
+	{   // APD.cu:2037-2042
+		float d0 = rc.c[0] - sc.c[0], d1 = rc.c[1] - sc.c[1], d2 = rc.c[2] - sc.c[2];
+		o.baseline = sqrtaf(fmaf(d2, d2, fmaf(d0, d0, d1 * d1)));
+	}
+	o.cam = sc;
+	vout[v] = o;
+}
+
+__global__ void k_pad_ref(const float *src, int W, int H, int src_pitch, float *dst, int dst_pitch, int rows) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= dst_pitch || y >= rows) return;
+	const int sx = min(max(x - kRefPad, 0), W - 1), sy = min(max(y - kRefPad, 0), H - 1);
+	dst[(size_t)y * dst_pitch + x] = src[(size_t)sy * src_pitch + sx];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1. curand_init(seed, subsequence = y, offset = x) for every pixel. The subsequence skip-ahead is
+// done once per row chunk; inside a chunk the state advances by one generator step per pixel,
+// which is what `offset` means for XORWOW.
+constexpr int kRngChunk = 32;
+__global__ void k_rng_seed(uint2 *rng, int W, int H, unsigned long long seed) {
+	const int chunks = (W + kRngChunk - 1) / kRngChunk;
+	const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= (long long)chunks * H) return;
+	const int y = (int)(gid / chunks), x0 = (int)(gid % chunks) * kRngChunk;
+	curandStateXORWOW_t st;
+	curand_init(seed, (unsigned long long)y, (unsigned long long)x0, &st);
+	Rng r; r.v0 = st.v[0]; r.v1 = st.v[1]; r.v2 = st.v[2]; r.v3 = st.v[3]; r.v4 = st.v[4]; r.d = st.d;
+	const int x1 = min(x0 + kRngChunk, W);
+	for (int x = x0; x < x1; ++x) {
+		rng_store(rng, (size_t)y * W + x, r);
+		(void)rng_next(r);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory staging of the reference tile (+5 px halo) and of the per-view constants.
+template <int TW, int TH>
+struct TileCfg {
+	static constexpr int PW = ((TW + 2 * kHalo + 3) / 4) * 4;   // row pitch, multiple of 16 B
+	static constexpr int PH = TH + 2 * kHalo;
+	static constexpr int ELEMS = PW * PH;
+};
+
+template <int TW, int TH, int NT>
+__device__ __forceinline__ void load_tile(const Args &a, float *tile, int x0, int y0, int tid) {
+	using C = TileCfg<TW, TH>;
+	const float *src = a.ref_pad + (size_t)(y0 - kHalo + kRefPad) * a.ref_pitch + (x0 - kHalo + kRefPad);
+	const int max_x = a.W + 2 * kRefPad - (x0 - kHalo + kRefPad);   // columns available to the right
+	const int max_y = a.H + 2 * kRefPad - (y0 - kHalo + kRefPad);
+	for (int i = tid; i < C::ELEMS; i += NT) {
+		const int ly = i / C::PW, lx = i - ly * C::PW;
+		float v = 0.f;
+		if (lx < max_x && ly < max_y) v = src[(size_t)ly * a.ref_pitch + lx];
+		tile[i] = v;
+	}
+}
+
+__device__ __forceinline__ void load_views(const Args &a, ViewConst *sv, RefConst *sr, int tid, int nt) {
+	const int n = a.S * (int)(sizeof(ViewConst) / 4);
+	const uint32_t *g = reinterpret_cast<const uint32_t *>(a.views);
+	uint32_t *s = reinterpret_cast<uint32_t *>(sv);
+	for (int i = tid; i < n; i += nt) s[i] = g[i];
+	const uint32_t *gr = reinterpret_cast<const uint32_t *>(a.ref);
+	uint32_t *srr = reinterpret_cast<uint32_t *>(sr);
+	for (int i = tid; i < (int)(sizeof(RefConst) / 4); i += nt) srr[i] = gr[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5. Full grid, 16x16 pixel tiles.
+constexpr int kFullTW = 16, kFullTH = 16, kFullNT = 256;
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kFullNT) k_init_planes(const Args a) {
+	using C = TileCfg<kFullTW, kFullTH>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float *tile = reinterpret_cast<float *>(smem_raw);
+	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
+	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
+	float *cm = reinterpret_cast<float *>(sv + a.S);          // [S][NT] costs of this pixel
+	const int tid = threadIdx.y * kFullTW + threadIdx.x;
+	const int x0 = blockIdx.x * kFullTW, y0 = blockIdx.y * kFullTH;
+	load_tile<kFullTW, kFullTH, kFullNT>(a, tile, x0, y0, tid);
+	load_views(a, sv, sr, tid, kFullNT);
+	__syncthreads();
+	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+	if (px >= a.W || py >= a.H) return;
+	const size_t center = (size_t)py * a.W + px;
+	const RefConst &rc = *sr;
+	const float xf = (float)px, yf = (float)py;
+	const int S = a.S;
+	const float inv36 = a.inv_w[0];
+	if (FIRST) {
+		Rng rng = rng_load(a.rng, center);
+		// GenerateRandomPlaneHypothesis, APD.cu:276-282
+		const float depth = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
+		float4 pl = random_normal(rc, xf, yf, rng, depth);
+		pl.w = plane_offset(rc, xf, yf, depth, pl.x, pl.y, pl.z);
+		rng_store(a.rng, center, rng);
+		a.planes[center] = pl;
+		// ComputeMultiViewInitialCostandSelectedViews, APD.cu:616-662
+		int valid = 0;
+		for (int v = 0; v < S; ++v) {
+			const Homog Hm = make_homography(rc, sv[v], pl);
+			const float c = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, threadIdx.x, threadIdx.y, px, py, inv36);
+			cm[v * kFullNT + tid] = c;
+			if (c < kCostMax) valid++;
+		}
+		const int top_k = min(valid, a.top_k);
+		uint32_t bits = 0u;
+		float cost = kCostMax;
+		if (top_k > 0) {
+			// the top_k smallest costs in ascending order == prefix of the reference's insertion sort
+			uint32_t taken = 0u;
+			float sum = 0.0f, last = 0.0f;
+			for (int r = 0; r < top_k; ++r) {
+				int best = -1; float bv = 0.f;
+				for (int v = 0; v < S; ++v) {
+					if ((taken >> v) & 1u) continue;
+					const float c = cm[v * kFullNT + tid];
+					if (best < 0 || c < bv) { best = v; bv = c; }
+				}
+				taken |= 1u << best;
+				sum += bv; last = bv;
+			}
+			for (int v = 0; v < S; ++v) if (cm[v * kFullNT + tid] <= last) bits |= 1u << v;
+			cost = sum * rcpf((float)top_k);
+		}
+		a.sel_views[center] = bits;
+		a.costs[center] = cost;
+	} else {
+		// prior (world normal, depth) -> plane in the reference camera frame, APD.cu:827-832
+		const float4 in = a.planes[center];
+		const float *R = rc.cam.R;
+		float4 pl;
+		pl.x = fmaf(in.z, R[2], fmaf(in.x, R[0], in.y * R[1]));
+		pl.y = fmaf(in.z, R[5], fmaf(in.x, R[3], in.y * R[4]));
+		pl.z = fmaf(in.z, R[8], fmaf(in.x, R[6], in.y * R[7]));
+		pl.w = plane_offset(rc, xf, yf, in.w, pl.x, pl.y, pl.z);
+		a.planes[center] = pl;
+		// ComputeMultiViewInitialCost, APD.cu:664-693 (incl. the unSetBit quirk :47-50)
+		uint32_t bits = a.sel_views[center];
+		int count = 0; float sum = 0.0f;
+		for (int v = 0; v < S; ++v) {
+			if (!((bits >> v) & 1u)) continue;
+			const Homog Hm = make_homography(rc, sv[v], pl);
+			const float c = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, threadIdx.x, threadIdx.y, px, py, inv36);
+			if (c < kCostMax) { count++; sum += c; }
+			else bits &= (0xFFFFFFFEu << v);
+		}
+		a.sel_views[center] = bits;
+		a.costs[center] = (count == 0) ? kCostMax : sum * rcpf((float)count);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6/K7. One colour of the checkerboard per launch; a block owns a 32x16 pixel tile (256 pixels of
+// that colour); a warp covers a 16x4 patch so that its texture footprint stays compact.
+constexpr int kHalfTW = 32, kHalfTH = 16;
+
+__device__ __forceinline__ void half_pixel(int tid, int x0, int y0, int color, int &px, int &py, int &lx, int &ly) {
+	const int warp = tid >> 5, lane = tid & 31;
+	lx = (warp & 1) * 16 + (lane & 15);
+	const int ybase = (warp >> 1) * 4 + 2 * (lane >> 4);
+	px = x0 + lx;
+	ly = ybase + ((px + y0 + ybase + color) & 1);
+	py = y0 + ly;
+}
+
+// smallest stored cost along a propagation arm (strict <, first wins), APD.cu:1022-1199
+struct ArmMin { float c; int pos; };
+__device__ __forceinline__ void arm_try(ArmMin &m, const float *costs, int pos) {
+	const float c = costs[pos];
+	if (c < m.c) { m.c = c; m.pos = pos; }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) k_strong(const Args a, const int iter, const int color) {
+	using C = TileCfg<kHalfTW, kHalfTH>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float *tile = reinterpret_cast<float *>(smem_raw);
+	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
+	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
+	float *cm = reinterpret_cast<float *>(sv + a.S);          // [9*S][NT]: 8xS cost matrix + S probabilities
+	const int tid = threadIdx.x;
+	const int x0 = blockIdx.x * kHalfTW, y0 = blockIdx.y * kHalfTH;
+	load_tile<kHalfTW, kHalfTH, NT>(a, tile, x0, y0, tid);
+	load_views(a, sv, sr, tid, NT);
+	__syncthreads();
+	int px, py, lx, ly;
+	half_pixel(tid, x0, y0, color, px, py, lx, ly);
+	if (px >= a.W || py >= a.H || py >= a.half_rows) return;
+	const int W = a.W, H = a.H, S = a.S;
+	const int center = py * W + px;
+	if (a.states[center] == APD_WEAK) return;
+	const RefConst &rc = *sr;
+	const float xf = (float)px, yf = (float)py;
+	const float inv36 = a.inv_w[0];
+	const float *costs = a.costs;
+	float *cmt = cm + tid;
+#define CM(k, v) cmt[((k) * S + (v)) * NT]
+#define PROB(v) cmt[(8 * S + (v)) * NT]
+
+	// ---- adaptive checkerboard sampling: 8 candidates (0 up_near 1 up_far 2 down_near 3 down_far
+	//      4 left_near 5 left_far 6 right_near 7 right_far)
+	int pos[8]; unsigned flags = 0u;
+	{
+		ArmMin m;
+		if (py > 2) { flags |= 2u; m.pos = center - 3 * W; m.c = costs[m.pos];
+			for (int i = 1; i < 11; ++i) if (py > 2 + 2 * i) arm_try(m, costs, center - 3 * W - 2 * i * W);
+			pos[1] = m.pos; }
+		if (py < H - 3) { flags |= 8u; m.pos = center + 3 * W; m.c = costs[m.pos];
+			for (int i = 1; i < 11; ++i) if (py < H - 3 - 2 * i) arm_try(m, costs, center + 3 * W + 2 * i * W);
+			pos[3] = m.pos; }
+		if (px > 2) { flags |= 32u; m.pos = center - 3; m.c = costs[m.pos];
+			for (int i = 1; i < 11; ++i) if (px > 2 + 2 * i) arm_try(m, costs, center - 3 - 2 * i);
+			pos[5] = m.pos; }
+		if (px < W - 3) { flags |= 128u; m.pos = center + 3; m.c = costs[m.pos];
+			for (int i = 1; i < 11; ++i) if (px < W - 3 - 2 * i) arm_try(m, costs, center + 3 + 2 * i);
+			pos[7] = m.pos; }
+		if (py > 0) { flags |= 1u; m.pos = center - W; m.c = costs[m.pos];
+			for (int i = 0; i < 3; ++i) {
+				if (py > 1 + i && px > i) arm_try(m, costs, center - W - (1 + i) * W - (1 + i));
+				if (py > 1 + i && px < W - 1 - i) arm_try(m, costs, center - W - (1 + i) * W + (1 + i));
+			}
+			pos[0] = m.pos; }
+		if (py < H - 1) { flags |= 4u; m.pos = center + W; m.c = costs[m.pos];
+			for (int i = 0; i < 3; ++i) {
+				if (py < H - 2 - i && px > i) arm_try(m, costs, center + W + (1 + i) * W - (1 + i));
+				if (py < H - 2 - i && px < W - 1 - i) arm_try(m, costs, center + W + (1 + i) * W + (1 + i));
+			}
+			pos[2] = m.pos; }
+		if (px > 0) { flags |= 16u; m.pos = center - 1; m.c = costs[m.pos];
+			for (int i = 0; i < 3; ++i) {
+				if (px > 1 + i && py > i) arm_try(m, costs, center - 1 - (1 + i) - (1 + i) * W);
+				if (px > 1 + i && py < H - 1 - i) arm_try(m, costs, center - 1 - (1 + i) + (1 + i) * W);
+			}
+			pos[4] = m.pos; }
+		if (px < W - 1) { flags |= 64u; m.pos = center + 1; m.c = costs[m.pos];
+			for (int i = 0; i < 3; ++i) {
+				if (px < W - 2 - i && py > i) arm_try(m, costs, center + 1 + (1 + i) - (1 + i) * W);
+				if (px < W - 2 - i && py < H - 1 - i) arm_try(m, costs, center + 1 + (1 + i) + (1 + i) * W);
+			}
+			pos[6] = m.pos; }
+	}
+
+	// ---- 8 x S matching costs. A missing candidate keeps the reference's partially initialised
+	//      row: `float cost_array[8][32] = {2.0f}` sets [0][0] only (APD.cu:1004)
+#pragma unroll 1
+	for (int k = 0; k < 8; ++k) {
+		if ((flags >> k) & 1u) {
+			const float4 pl = a.planes[pos[k]];
+#pragma unroll 1
+			for (int v = 0; v < S; ++v) {
+				const Homog Hm = make_homography(rc, sv[v], pl);
+				CM(k, v) = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, lx, ly, px, py, inv36);
+			}
+		} else {
+			for (int v = 0; v < S; ++v) CM(k, v) = (k == 0 && v == 0) ? 2.0f : 0.0f;
+		}
+	}
+
+	// ---- multi-hypothesis joint view selection, APD.cu:1203-1259
+	const float thr = 0.8 * __expf((float)(unsigned)(iter * iter) * -0.011111111380159854889f);
+	const float thr_fallback = __expf((thr * thr) * -3.125f);
+	uint32_t nb_bits[4]; unsigned nb_ok = 0u;
+	{
+		const int nb_pos[4] = {center - W, center + W, center - 1, center + 1};
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			nb_bits[i] = 0u;
+			if ((flags >> (2 * i)) & 1u) { nb_ok |= 1u << i; nb_bits[i] = a.sel_views[nb_pos[i]]; }
+		}
+	}
+	float prob_sum = 0.0f;
+	for (int v = 0; v < S; ++v) {
+		float prior = 0.0f;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			if ((nb_ok >> i) & 1u) prior += ((nb_bits[i] >> v) & 1u) ? 0.9f : 0.1f;
+		float count = 0.0f, tmpw = 0.0f; int count_false = 0;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const float c = CM(k, v);
+			if (c < thr) { tmpw += __expf((c * c) * -5.5555553436279296875f); count += 1.0f; }
+			if (c > 1.2f) count_false++;
+		}
+		float p = 0.0f;
+		if (count > 2.0f && count_false < 3) p = tmpw * rcpf(count);
+		else if (count_false < 3) p = thr_fallback;
+		p = p * prior;
+		PROB(v) = p;
+		prob_sum += p;
+	}
+	Rng rng = rng_load(a.rng, center);
+	VW vw; vw.lo = 0ull; vw.hi = 0ull;
+	{
+		const float inv = rcpf(prob_sum);
+		float cum = 0.0f;
+		for (int v = 0; v < S; ++v) { cum = fmaf(inv, PROB(v), cum); PROB(v) = cum; }   // TransformPDFToCDF
+		for (int s = 0; s < 15; ++s) {
+			const float r = rng_uniform(rng) - 1.1920928955078125e-07f;
+			for (int v = 0; v < S; ++v) if (PROB(v) > r) { vw_add(vw, v); break; }
+		}
+	}
+	uint32_t temp_sel = 0u; float weight_norm = 0.0f;
+	for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) { temp_sel |= 1u << v; weight_norm += (float)w; } }
+	const float inv_wn = rcpf(weight_norm);
+
+	float best_cost; int best_k;
+	{
+		float fc[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			float acc = 0.0f;
+			for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) acc = fmaf((float)w, CM(k, v), acc); }
+			fc[k] = acc * inv_wn;
+		}
+		best_cost = fc[0]; best_k = 0;            // FindMinCostIndex: `<=`, last minimum wins (APD.cu:29-40)
+#pragma unroll
+		for (int k = 1; k < 8; ++k) if (fc[k] <= best_cost) { best_cost = fc[k]; best_k = k; }
+	}
+
+	// ---- current hypothesis under the sampled views (views with weight 0 contribute exactly 0)
+	float4 pl_now = a.planes[center];
+	float cost_now;
+	{
+		float acc = 0.0f;
+		for (int v = 0; v < S; ++v) {
+			const int w = vw_get(vw, v);
+			if (w == 0) continue;
+			const Homog Hm = make_homography(rc, sv[v], pl_now);
+			acc = fmaf((float)w, ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, lx, ly, px, py, inv36), acc);
+		}
+		cost_now = acc * inv_wn;
+	}
+	const float cost_stored = cost_now;                   // costs[center] = cost_now (APD.cu:1295)
+	float depth_now = plane_depth(rc, pl_now, xf, yf);
+	uint32_t sel_out = 0u; bool sel_write = false;
+	if ((flags >> best_k) & 1u) {
+		int bp = pos[0];
+#pragma unroll
+		for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
+		const float4 cand = a.planes[bp];
+		const float d = plane_depth(rc, cand, xf, yf);
+		if (d >= a.depth_min && d <= a.depth_max && best_cost < cost_now) {
+			depth_now = d; pl_now = cand; cost_now = best_cost; sel_out = temp_sel; sel_write = true;
+		}
+	}
+
+	// ---- PlaneHypothesisRefinementStrong, APD.cu:837-890
+	{
+		const float depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
+		const float4 n_rand = random_normal(rc, xf, yf, rng, depth_now);
+		const float lo = depth_now * (1.0f - 0.02f);
+		const float span = fmaf(depth_now, 1.0f + 0.02f, -lo);
+		const float depth_pert = fmaf(span, rng_uniform(rng), lo);     // the do/while never repeats (:860-862)
+		const float4 n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
+		const float4 n0 = pl_now; const float d0 = depth_now;
+#pragma unroll 1
+		for (int i = 0; i < 5; ++i) {
+			const float di = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : d0);
+			float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
+			t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
+			float acc = 0.0f;
+			for (int v = 0; v < S; ++v) {
+				const int w = vw_get(vw, v);
+				if (w == 0) continue;
+				const Homog Hm = make_homography(rc, sv[v], t);
+				acc = fmaf((float)w, ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, lx, ly, px, py, inv36), acc);
+			}
+			const float tc = acc * inv_wn;
+			const float d = plane_depth(rc, t, xf, yf);
+			if (d >= a.depth_min && d <= a.depth_max && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+		}
+	}
+	rng_store(a.rng, center, rng);
+	vw_store(a.view_w, center, vw);
+	if (sel_write) a.sel_views[center] = sel_out;
+	if (a.state == APD_REFINE_INIT) {
+		if ((double)cost_now < (double)cost_stored - 0.1) { a.costs[center] = cost_now; a.planes[center] = pl_now; }
+		else a.costs[center] = cost_stored;
+	} else {
+		a.costs[center] = cost_now; a.planes[center] = pl_now;
+	}
+#undef CM
+#undef PROB
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11
+__global__ void k_depth_normal(const Args a) {
+	const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+	if (px >= a.W || py >= a.H) return;
+	const size_t center = (size_t)py * a.W + px;
+	const RefConst rc = *a.ref;
+	const float4 pl = a.planes[center];
+	const float depth = plane_depth(rc, pl, (float)px, (float)py);
+	const float *R = rc.cam.R;
+	float4 o;   // TransformNormal, APD.cu:374-382 (R^T n)
+	o.x = fmaf(pl.z, R[6], fmaf(pl.x, R[0], pl.y * R[3]));
+	o.y = fmaf(pl.z, R[7], fmaf(pl.x, R[1], pl.y * R[4]));
+	o.z = fmaf(pl.z, R[8], fmaf(pl.x, R[2], pl.y * R[5]));
+	o.w = depth;
+	a.planes[center] = o;
+}
+
+// K12/K13: median of own depth and up to 20 STRONG opposite-colour neighbours, APD.cu:1604-1714
+__global__ void k_median(const Args a, const int color) {
+	const int px = blockIdx.x * blockDim.x + threadIdx.x;
+	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+	const int py = 2 * yy + ((px + color) & 1);
+	const int W = a.W, H = a.H;
+	if (px >= W || py >= H || py >= a.half_rows) return;
+	const int center = py * W + px;
+	if (a.states[center] == APD_WEAK) return;
+	if (a.costs[center] < 0.001f) return;
+	float f[21]; int n = 0;
+	f[n++] = a.planes[center].w;
+	const int dx[20] = {0, 0, 0, 0, 0, 0, -1, -3, -5, 1, 3, 5, 2, 2, -2, -2, -1, 1, -1, 1};
+	const int dy[20] = {-1, -3, -5, 1, 3, 5, 0, 0, 0, 0, 0, 0, -1, 1, -1, 1, -2, -2, 2, 2};
+#pragma unroll
+	for (int k = 0; k < 20; ++k) {
+		const int x = px + dx[k], y = py + dy[k];
+		// the reference's bounds (APD.cu:1642-1703): identical to "inside the image" except for the
+		// two (+-1, -2) taps which demand `p.y > 2` (APD.cu:1691, :1695)
+		bool ok = x >= 0 && x < W && y >= 0 && y < H;
+		if (dy[k] == -2) ok = ok && (py > 2);
+		if (ok && a.states[y * W + x] == APD_STRONG) f[n++] = a.planes[y * W + x].w;
+	}
+	for (int i = 1; i < n; ++i) {   // sort_small
+		const float t = f[i]; int j = i;
+		for (; j >= 1 && t < f[j - 1]; --j) f[j] = f[j - 1];
+		f[j] = t;
+	}
+	const int m = n / 2;
+	a.planes[center].w = (n % 2 == 0) ? (f[m - 1] + f[m]) * 0.5f : f[m];
+}
+
+// ------------------------------------------------------------------------------------------------
+// ComputeGeomConsistencyCost, APD.cu:752-789
+__device__ __forceinline__ float geom_cost(const Args &a, const RefConst &rc, const ViewConst &vc, int layer, const float4 pl, float xf, float yf) {
+	const float depth = plane_depth(rc, pl, xf, yf);
+	float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
+	const float *R = rc.cam.R;
+	float Px = rc.cam.c[0] + fmaf(R[6], depth, fmaf(R[0], X0, R[3] * X1));
+	float Py = rc.cam.c[1] + fmaf(R[7], depth, fmaf(R[1], X0, R[4] * X1));
+	float Pz = rc.cam.c[2] + fmaf(R[8], depth, fmaf(R[2], X0, R[5] * X1));
+	const apd_camera &s = vc.cam;
+	float tx = s.t[0] + fmaf(s.R[2], Pz, fmaf(s.R[0], Px, s.R[1] * Py));
+	float ty = s.t[1] + fmaf(s.R[5], Pz, fmaf(s.R[3], Px, s.R[4] * Py));
+	float tz = s.t[2] + fmaf(s.R[8], Pz, fmaf(s.R[6], Px, s.R[7] * Py));
+	float rd = rcpf(fmaf(s.K[8], tz, fmaf(s.K[6], tx, s.K[7] * ty)));
+	float sx = fmaf(s.K[2], tz, fmaf(s.K[0], tx, s.K[1] * ty)) * rd;
+	float sy = fmaf(s.K[5], tz, fmaf(s.K[3], tx, s.K[4] * ty)) * rd;
+	const float sd = tex2DLayered<float>(a.depth_tex, (float)(int)sx + 0.5f, (float)(int)sy + 0.5f, layer);
+	if (sd == 0.0f) return 3.0f;
+	const float rsK0 = rcpf(s.K[0]), rsK4 = rcpf(s.K[4]);
+	float Y0 = (sd * (sx - s.K[2])) * rsK0;
+	float Y1 = (sd * (sy - s.K[5])) * rsK4;
+	float Qx = s.c[0] + fmaf(s.R[6], sd, fmaf(s.R[0], Y0, s.R[3] * Y1));
+	float Qy = s.c[1] + fmaf(s.R[7], sd, fmaf(s.R[1], Y0, s.R[4] * Y1));
+	float Qz = s.c[2] + fmaf(s.R[8], sd, fmaf(s.R[2], Y0, s.R[5] * Y1));
+	const float *K = rc.cam.K; const float *t = rc.cam.t;
+	float ux = t[0] + fmaf(R[2], Qz, fmaf(R[0], Qx, R[1] * Qy));
+	float uy = t[1] + fmaf(R[5], Qz, fmaf(R[3], Qx, R[4] * Qy));
+	float uz = t[2] + fmaf(R[8], Qz, fmaf(R[6], Qx, R[7] * Qy));
+	float rb = rcpf(fmaf(K[8], uz, fmaf(K[6], ux, K[7] * uy)));
+	float dc = fmaf(-fmaf(K[2], uz, fmaf(K[0], ux, K[1] * uy)), rb, xf);
+	float dr = fmaf(-fmaf(K[5], uz, fmaf(K[3], ux, K[4] * uy)), rb, yf);
+	return fminf(sqrtaf(fmaf(dc, dc, dr * dr)), 3.0f);
+}
+
+// Shared front end of K14 and K15: plane back into the reference camera frame, mean baseline and
+// summed weights over the selected views (APD.cu:2012-2052, :2160-2199).
+struct SweepCtx { float4 pl; float depth, weight_normal, kb, disp; int valid; };
+__device__ __forceinline__ bool sweep_setup(const Args &a, const RefConst &rc, const ViewConst *sv, size_t center, uint32_t bits, const VW &vw, SweepCtx &c) {
+	const float4 in = a.planes[center];
+	const float *R = rc.cam.R;
+	c.pl.x = fmaf(in.z, R[2], fmaf(in.x, R[0], in.y * R[1]));
+	c.pl.y = fmaf(in.z, R[5], fmaf(in.x, R[3], in.y * R[4]));
+	c.pl.z = fmaf(in.z, R[8], fmaf(in.x, R[6], in.y * R[7]));
+	c.pl.w = in.w; c.depth = in.w;
+	if (c.depth == 0.0f) return false;
+	float base = 0.0f; c.weight_normal = 0.0f; c.valid = 0;
+	for (int v = 0; v < a.S; ++v) if ((bits >> v) & 1u) { base += sv[v].baseline; c.weight_normal += (float)vw_get(vw, v); c.valid++; }
+	if (c.valid == 0) return true;
+	base = rcpf((float)c.valid) * base;
+	c.kb = base * rc.cam.K[0];
+	c.disp = c.kb * rcpf(c.depth);
+	return true;
+}
+
+// weighted multi-view cost of the pixel's plane moved to depth `d` (APD.cu:2067-2081)
+template <bool K15_FORM>
+__device__ __forceinline__ float sweep_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float *tile, int pitch,
+                                            int lx, int ly, int px, int py, const SweepCtx &c, uint32_t bits, const VW &vw, float d) {
+	const float xf = (float)px, yf = (float)py;
+	const float inv36 = a.inv_w[0];
+	float4 t = c.pl;
+	t.w = plane_offset(rc, xf, yf, d, t.x, t.y, t.z);
+	float acc = 0.0f;
+	for (int v = 0; v < a.S; ++v) {
+		if (!((bits >> v) & 1u)) continue;
+		const int w = vw_get(vw, v);
+		if (w == 0) continue;                    // multiplied by a zero weight in the reference
+		const Homog Hm = make_homography(rc, sv[v], t);
+		float tc = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, pitch, lx, ly, px, py, inv36);
+		if (K15_FORM) {   // APD.cu:2217-2220
+			acc = fmaf((float)w, tc, acc);
+			if (a.geom) acc = fmaf((float)w, a.geom_factor * geom_cost(a, rc, sv[v], v + 1, t, xf, yf), acc);
+		} else {          // APD.cu:2074-2078
+			if (a.geom) tc = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, t, xf, yf), tc);
+			acc = fmaf((float)w, tc, acc);
+		}
+	}
+	return acc;
+}
+
+// K14: reliable-pixel classification
+__global__ void __launch_bounds__(kFullNT) k_classify(const Args a) {
+	using C = TileCfg<kFullTW, kFullTH>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float *tile = reinterpret_cast<float *>(smem_raw);
+	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
+	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
+	float *prof = reinterpret_cast<float *>(sv + a.S);        // [61][NT] cost profile
+	const int tid = threadIdx.y * kFullTW + threadIdx.x;
+	const int x0 = blockIdx.x * kFullTW, y0 = blockIdx.y * kFullTH;
+	load_tile<kFullTW, kFullTH, kFullNT>(a, tile, x0, y0, tid);
+	load_views(a, sv, sr, tid, kFullNT);
+	__syncthreads();
+	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+	if (px >= a.W || py >= a.H) return;
+	const size_t center = (size_t)py * a.W + px;
+	if (px < 6 || py < 6 || px >= a.W - 6 || py >= a.H - 6) { a.states[center] = APD_UNKNOWN; return; }
+	const RefConst &rc = *sr;
+	const uint32_t bits = a.sel_views[center];
+	const VW vw = vw_load(a.view_w, center);
+	SweepCtx c;
+	if (!sweep_setup(a, rc, sv, center, bits, vw, c) || c.valid == 0) { a.states[center] = APD_UNKNOWN; return; }
+	const float inv_wn = rcpf(c.weight_normal);
+	float *p = prof + tid;
+	for (int k = -30; k <= 30; ++k) {
+		const float d = c.kb * rcpf(c.disp + (float)k);
+		float pc = 2.0f;
+		if (!(d < a.depth_min || d > a.depth_max)) {
+			pc = sweep_cost<false>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, d) * inv_wn;
+			pc = (2.0f > pc) ? pc : 2.0f;       // OpenCV MIN(2.0f, p_cost)
+		}
+		p[(k + 30) * kFullNT] = pc;
+	}
+	// peak analysis, APD.cu:2092-2143
+	int peak_count = 0, min_peak = 0; float min_cost = 2.0f;
+	unsigned long long peaks = 0ull;
+	for (int i = 2; i < 59; ++i) {
+		const float ci = p[i * kFullNT];
+		if (p[(i - 1) * kFullNT] > ci && p[(i + 1) * kFullNT] > ci) {
+			peaks |= 1ull << i; peak_count++;
+			if (ci < min_cost) { min_peak = i; min_cost = ci; }
+		}
+	}
+	uint8_t out;
+	if (abs(min_peak - 30) > a.weak_peak_radius || p[min_peak * kFullNT] > 0.5f) out = APD_WEAK;
+	else if (peak_count == 1) out = (p[min_peak * kFullNT] <= 0.15f) ? APD_STRONG : APD_WEAK;
+	else {
+		float var = 0.0f;
+		for (int i = 2; i < 59; ++i) if (((peaks >> i) & 1ull) && i != min_peak) { const float d = p[i * kFullNT] - min_cost; var = fmaf(d, d, var); }
+		var = sqrtaf(var) * rcpf((float)(peak_count - 1));
+		out = (var > 0.2f) ? APD_STRONG : APD_WEAK;
+	}
+	a.states[center] = out;
+}
+
+// K15
+__global__ void __launch_bounds__(kFullNT) k_local_refine(const Args a) {
+	using C = TileCfg<kFullTW, kFullTH>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float *tile = reinterpret_cast<float *>(smem_raw);
+	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
+	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
+	const int tid = threadIdx.y * kFullTW + threadIdx.x;
+	const int x0 = blockIdx.x * kFullTW, y0 = blockIdx.y * kFullTH;
+	load_tile<kFullTW, kFullTH, kFullNT>(a, tile, x0, y0, tid);
+	load_views(a, sv, sr, tid, kFullNT);
+	__syncthreads();
+	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+	if (px >= a.W || py >= a.H) return;
+	const size_t center = (size_t)py * a.W + px;
+	const RefConst &rc = *sr;
+	const uint32_t bits = a.sel_views[center];
+	const VW vw = vw_load(a.view_w, center);
+	SweepCtx c;
+	if (!sweep_setup(a, rc, sv, center, bits, vw, c)) return;
+	if (c.weight_normal == 0.0f || c.valid == 0) return;
+	// cost of the current depth, APD.cu:2176-2182 (K14's accumulation form)
+	const float cost_sum = sweep_cost<false>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, c.depth);
+	const float inv_wn = rcpf(c.weight_normal);
+	float min_cost = 2.0f, best_depth = c.depth;
+	for (int k = -5; k <= 5; ++k) {
+		const float d = c.kb * rcpf(c.disp + (float)k);
+		if (d < a.depth_min || d > a.depth_max) continue;
+		const float tc = sweep_cost<true>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, d) * inv_wn;
+		if (tc < min_cost) { min_cost = tc; best_depth = d; }
+	}
+	const float diff = fmaf(inv_wn, cost_sum, -min_cost);   // (cost_now / weight_normal) - min_cost, one FFMA
+	if ((double)diff > 0.1) a.planes[center].w = best_depth;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+static inline size_t smem_common(int S) { return sizeof(RefConst) + (size_t)S * sizeof(ViewConst); }
+
+void launch_setup_views(cudaStream_t st, const apd_camera *cams, int S, ViewConst *v, RefConst *r, float *inv_w) {
+	k_setup_views<<<1, 32, 0, st>>>(cams, S, v, r, inv_w);
+}
+void launch_pad_ref(cudaStream_t st, const float *src, int W, int H, int src_pitch, float *dst, int dst_pitch, int rows) {
+	dim3 b(32, 8), g((dst_pitch + 31) / 32, (rows + 7) / 8);
+	k_pad_ref<<<g, b, 0, st>>>(src, W, H, src_pitch, dst, dst_pitch, rows);
+}
+void launch_rng_seed(cudaStream_t st, const Args &a, unsigned long long seed) {
+	const long long n = (long long)((a.W + kRngChunk - 1) / kRngChunk) * a.H;
+	k_rng_seed<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a.rng, a.W, a.H, seed);
+}
+cudaError_t launch_init_planes(cudaStream_t st, const Args &a) {
+	using C = TileCfg<kFullTW, kFullTH>;
+	const size_t smem = C::ELEMS * 4 + smem_common(a.S) + (size_t)a.S * kFullNT * 4;
+	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
+	if (a.state == APD_FIRST_INIT) {
+		cudaFuncSetAttribute(k_init_planes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_init_planes<true><<<g, b, smem, st>>>(a);
+	} else {
+		cudaFuncSetAttribute(k_init_planes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		k_init_planes<false><<<g, b, smem, st>>>(a);
+	}
+	return cudaGetLastError();
+}
+cudaError_t launch_strong(cudaStream_t st, const Args &a, int iter, int color) {
+	using C = TileCfg<kHalfTW, kHalfTH>;
+	constexpr int NT = 256;
+	const size_t smem = C::ELEMS * 4 + smem_common(a.S) + (size_t)9 * a.S * NT * 4;
+	if (smem > 227 * 1024) return cudaErrorInvalidValue;
+	cudaFuncSetAttribute(k_strong<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	dim3 g((a.W + kHalfTW - 1) / kHalfTW, (a.H + kHalfTH - 1) / kHalfTH);
+	k_strong<NT><<<g, NT, smem, st>>>(a, iter, color);
+	return cudaGetLastError();
+}
+void launch_depth_normal(cudaStream_t st, const Args &a) {
+	dim3 b(32, 8), g((a.W + 31) / 32, (a.H + 7) / 8);
+	k_depth_normal<<<g, b, 0, st>>>(a);
+}
+void launch_median(cudaStream_t st, const Args &a, int color) {
+	dim3 b(32, 8), g((a.W + 31) / 32, ((a.H + 1) / 2 + 7) / 8);
+	k_median<<<g, b, 0, st>>>(a, color);
+}
+cudaError_t launch_classify(cudaStream_t st, const Args &a) {
+	using C = TileCfg<kFullTW, kFullTH>;
+	const size_t smem = C::ELEMS * 4 + smem_common(a.S) + (size_t)61 * kFullNT * 4;
+	cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
+	k_classify<<<g, b, smem, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_local_refine(cudaStream_t st, const Args &a) {
+	using C = TileCfg<kFullTW, kFullTH>;
+	const size_t smem = C::ELEMS * 4 + smem_common(a.S);
+	cudaFuncSetAttribute(k_local_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
+	k_local_refine<<<g, b, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+}  // namespace apd
