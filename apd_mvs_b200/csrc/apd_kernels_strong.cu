@@ -554,13 +554,20 @@ __device__ __forceinline__ bool sweep_setup(const Args &a, const RefConst &rc, c
 }
 
 // weighted multi-view cost of the pixel's plane moved to depth `d` (APD.cu:2067-2081)
-template <bool K15_FORM>
+template <bool K15_FORM, bool HOISTED_Z = false>
 __device__ __forceinline__ float sweep_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float *tile, int pitch,
                                             int lx, int ly, int px, int py, const SweepCtx &c, uint32_t bits, const VW &vw, float d) {
 	const float xf = (float)px, yf = (float)py;
 	const float inv36 = a.inv_w[0];
 	float4 t = c.pl;
-	t.w = plane_offset(rc, xf, yf, d, t.x, t.y, t.z);
+	if (HOISTED_Z) {
+		// LocalRefine's first loop (APD.cu:2173-2177): the compiler hoists normal.z * depth out of the
+		// view loop as a rounded product, so the plane offset there is -((d*nz) + fma(X0,nx,X1*ny))
+		float X0, X1; backproject(rc, xf, yf, d, X0, X1);
+		t.w = -((d * t.z) + fmaf(X0, t.x, X1 * t.y));
+	} else {
+		t.w = plane_offset(rc, xf, yf, d, t.x, t.y, t.z);
+	}
 	float acc = 0.0f;
 	for (int v = 0; v < a.S; ++v) {
 		if (!((bits >> v) & 1u)) continue;
@@ -656,7 +663,7 @@ __global__ void __launch_bounds__(kFullNT) k_local_refine(const Args a) {
 	if (!sweep_setup(a, rc, sv, center, bits, vw, c)) return;
 	if (c.weight_normal == 0.0f || c.valid == 0) return;
 	// cost of the current depth, APD.cu:2176-2182 (K14's accumulation form)
-	const float cost_sum = sweep_cost<false>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, c.depth);
+	const float cost_sum = sweep_cost<false, true>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, c.depth);
 	const float inv_wn = rcpf(c.weight_normal);
 	float min_cost = 2.0f, best_depth = c.depth;
 	for (int k = -5; k <= 5; ++k) {
