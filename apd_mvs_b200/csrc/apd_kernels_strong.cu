@@ -221,12 +221,17 @@ __global__ void __launch_bounds__(kFullNT) k_init_planes(const Args a) {
 constexpr int kHalfTW = 32, kHalfTH = 16;
 
 __device__ __forceinline__ void half_pixel(int tid, int x0, int y0, int color, int &px, int &py, int &lx, int &ly) {
+	// Lanes 4q..4q+3 (one texture quad) own the four same-colour pixels of a 4x2 block, a diamond
+	// (x,y) (x+2,y) (x+1,y+1) (x+3,y+1): measured on B200 (tools/tex_probe3.cu) a quad whose four
+	// bilinear footprints stay within ~4x2 texels streams at the full 4 fetches/clk/SM, whereas four
+	// pixels of one row at stride 2 reach only 66 % of that. 8 quads = 16x4 pixels per warp.
 	const int warp = tid >> 5, lane = tid & 31;
-	lx = (warp & 1) * 16 + (lane & 15);
-	const int ybase = (warp >> 1) * 4 + 2 * (lane >> 4);
-	px = x0 + lx;
-	ly = ybase + ((px + y0 + ybase + color) & 1);
+	const int q = lane >> 2, k = lane & 3;
+	ly = (warp >> 1) * 4 + (q >> 2) * 2 + (k >> 1);
 	py = y0 + ly;
+	const int xb = (warp & 1) * 16 + (q & 3) * 4 + 2 * (k & 1);
+	lx = xb + ((x0 + xb + py + color) & 1);
+	px = x0 + lx;
 }
 
 // smallest stored cost along a propagation arm (strict <, first wins), APD.cu:1022-1199
