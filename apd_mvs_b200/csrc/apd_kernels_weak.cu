@@ -1,9 +1,577 @@
-// placeholder, replaced below
+// sm_100a kernels of the adaptive patch deformation path (pixels whose state is WEAK):
+//   k_row_nearest + k_nearest_strong   K2  FindNearestStrongPoint   APD.cu:2234-2270
+//   k_gen_anchors                      K3  GenNeighbours            APD.cu:1750-1969
+//   k_demote_unreliable                K4  NeigbourUpdate           APD.cu:1971-1987
+//   k_fit_plane                        K8  RANSACToGetFitPlane      APD.cu:2272-2384
+//   k_weak                             K9/K10 Black/RedPixelUpdateWeak APD.cu:1510-1545 -> :1323-1508
+//                                          -> :892-980, deformable NCC :400-528
+// Numerics follow the same contract as apd_device.cuh (explicit FMAs where the reference SASS has them).
+#include <cfloat>
 #include "apd_device.cuh"
+
 namespace apd {
-cudaError_t launch_nearest_strong(cudaStream_t, const Args &) { return cudaErrorNotSupported; }
-cudaError_t launch_gen_anchors(cudaStream_t, const Args &) { return cudaErrorNotSupported; }
-cudaError_t launch_demote_unreliable(cudaStream_t, const Args &) { return cudaErrorNotSupported; }
-cudaError_t launch_fit_plane(cudaStream_t, const Args &) { return cudaErrorNotSupported; }
-cudaError_t launch_weak(cudaStream_t, const Args &, int, int) { return cudaErrorNotSupported; }
+
+struct AnchorConsts { float cos_a, sin_a, thresh; int shift_range; };
+void launch_anchor_consts(cudaStream_t st, int rotate_time, AnchorConsts *out);   // apd_anchor_consts.cu (fast-math TU)
+
+// ------------------------------------------------------------------------------------------------
+// K2. The reference scans a 201x201 window per WEAK pixel (40 401 loads) for the nearest STRONG pixel,
+// ties broken by scan order (dx ascending, then dy ascending, strict <). Exact two-pass equivalent:
+// (1) per pixel, signed dx of the nearest STRONG pixel of its own row within |dx| <= 100, the
+// negative one on ties; (2) per WEAK pixel, minimum over the 201 rows of (dx^2+dy^2, dx, dy).
+constexpr int kNearR = 100;
+__global__ void k_row_nearest(const uint8_t *states, int W, int H, int8_t *rowdx) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= W || y >= H) return;
+	const uint8_t *row = states + (size_t)y * W;
+	int8_t best = 127;
+	for (int d = 0; d <= kNearR; ++d) {
+		if (x - d >= 0 && row[x - d] == APD_STRONG) { best = (int8_t)(-d); break; }
+		if (x + d < W && row[x + d] == APD_STRONG) { best = (int8_t)d; break; }
+	}
+	rowdx[(size_t)y * W + x] = best;
 }
+__global__ void k_nearest_strong(const Args a, const int8_t *rowdx) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= a.W || y >= a.H) return;
+	const size_t c = (size_t)y * a.W + x;
+	short2 out = make_short2(-1, -1);
+	if (a.states[c] == APD_WEAK) {
+		int best_d2 = 0x7fffffff, best_dx = 0, best_dy = 0;
+		for (int dy = -kNearR; dy <= kNearR; ++dy) {
+			const int yy = y + dy;
+			if (yy < 0 || yy >= a.H) continue;
+			const int dx = rowdx[(size_t)yy * a.W + x];
+			if (dx == 127) continue;
+			const int d2 = dx * dx + dy * dy;
+			if (d2 < best_d2 || (d2 == best_d2 && dx < best_dx)) { best_d2 = d2; best_dx = dx; best_dy = dy; }
+		}
+		if (best_d2 != 0x7fffffff) out = make_short2((short)(x + best_dx), (short)(y + best_dy));
+	}
+	a.nearest[c] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void normalize2(float &x, float &y) {   // NormalizeVec2, APD.cu:135-141
+	const float r = rsqrtaf(fmaf(x, x, y * y));
+	x *= r; y *= r;
+}
+__device__ __forceinline__ float3 point3(const RefConst &rc, int x, int y, float depth) {   // Get3DPoint, APD.cu:159-171
+	float X0, X1; backproject(rc, (float)x, (float)y, depth, X0, X1);
+	return make_float3(X0, X1, depth);
+}
+// PointinTriangle, APD.cu:91-112
+__device__ __forceinline__ bool point_in_triangle(short2 A, short2 B, short2 C, int px, int py) {
+	const float abx = (float)(B.x - A.x), aby = (float)(B.y - A.y);
+	const float bcx = (float)(C.x - B.x), bcy = (float)(C.y - B.y);
+	const float cax = (float)(A.x - C.x), cay = (float)(A.y - C.y);
+	const float ab = sqrtaf(fmaf(abx, abx, aby * aby)), bc = sqrtaf(fmaf(bcx, bcx, bcy * bcy)), ca = sqrtaf(fmaf(cax, cax, cay * cay));
+	if (ab <= 2.0f || bc <= 2.0f || ca <= 2.0f) return false;
+	if (!(ab + bc > ca && bc + ca > ab && ab + ca > bc)) return false;
+	const float pax = (float)(A.x - px), pay = (float)(A.y - py);
+	const float pbx = (float)(B.x - px), pby = (float)(B.y - py);
+	const float pcx = (float)(C.x - px), pcy = (float)(C.y - py);
+	const float t1 = fmaf(pax, pby, -(pay * pbx));
+	const float t2 = fmaf(pbx, pcy, -(pby * pcx));
+	const float t3 = fmaf(pcx, pay, -(pcy * pax));
+	return t1 * t2 >= 0.0f && t1 * t3 >= 0.0f;
+}
+// plane through three points, unit normal + offset (APD.cu:1897-1907, 2338-2349); false if degenerate
+__device__ __forceinline__ bool plane_from_points(const float3 A, const float3 B, const float3 C, float4 &pl) {
+	const float acx = A.x - C.x, acy = A.y - C.y, acz = A.z - C.z;
+	const float bcx = B.x - C.x, bcy = B.y - C.y, bcz = B.z - C.z;
+	float cx = fmaf(acy, bcz, -(bcy * acz));
+	float cy = -fmaf(acx, bcz, -(bcx * acz));
+	float cz = fmaf(acx, bcy, -(bcx * acy));
+	if ((cx == 0.0f && cy == 0.0f && cz == 0.0f) || isnan(cx) || isnan(cy) || isnan(cz)) return false;
+	normalize3(cx, cy, cz);
+	const float d = fmaf(cz, A.z, fmaf(cx, A.x, cy * A.y));
+	pl = make_float4(cx, cy, cz, -d);
+	return true;
+}
+__device__ __forceinline__ float plane_dist(const float4 pl, const float3 p) {
+	return fabsf(fmaf(pl.z, p.z, fmaf(pl.x, p.x, pl.y * p.y)) + pl.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3. One thread per WEAK pixel: deformable-anchor search along 8 base directions x rotate_time
+// sub-rotations, then a 50-iteration RANSAC plane through the anchors' 3-D points.
+__global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorConsts *acp) {
+	const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+	if (px >= a.W || py >= a.H) return;
+	const int W = a.W, H = a.H;
+	const size_t n = (size_t)W * H;
+	const int center = py * W + px;
+	if (a.states[center] != APD_WEAK) return;
+	const AnchorConsts ac = *acp;
+	const RefConst rc = *a.ref;
+	for (int k = 0; k < APD_NEIGHBOUR_NUM; ++k) a.anchors[(size_t)k * n + center] = make_short2(-1, -1);
+	a.anchors[center] = make_short2((short)px, (short)py);
+	Rng rng = rng_load(a.rng, center);
+	short2 sp[32]; unsigned valid = 0u; int found = 0;
+	for (int i = 0; i < 32; ++i) sp[i] = make_short2(-1, -1);
+	const float pxf = (float)px, pyf = (float)py, Wf = (float)W, Hf = (float)H;
+	const unsigned range = (unsigned)ac.shift_range;
+	int base = -1;
+	for (int ox = -1; ox <= 1; ++ox) for (int oy = -1; oy <= 1; ++oy) {
+		if (ox == 0 && oy == 0) continue;
+		float dx = (float)ox, dy = (float)oy;
+		normalize2(dx, dy);
+		++base;
+		for (int rot = 0; rot < a.rotate_time; ++rot) {
+			const int di = base * 4 + rot;
+			for (int radius = 2; radius <= APD_MAX_SEARCH_RADIUS; radius = min(radius * 2, radius + 25)) {
+				const float rf = (float)radius;
+				const float tx = fmaf(rf, dx, pxf), ty = fmaf(rf, dy, pyf);
+				if (tx < 0.0f || ty < 0.0f || tx >= Wf || ty >= Hf) break;
+				for (int t = 0; t < 4; ++t) {
+					// (curand()%2==0 ? 1 : -1) * curand() % shift_range, all in unsigned arithmetic (APD.cu:1813-1814)
+					const uint32_t d1 = rng_next(rng), d2 = rng_next(rng), d3 = rng_next(rng), d4 = rng_next(rng);
+					const uint32_t xs = (((d1 & 1u) == 0u) ? d2 : (0u - d2)) % range;
+					const uint32_t ys = (((d3 & 1u) == 0u) ? d4 : (0u - d4)) % range;
+					float ddx = fmaf(dx, 20.0f, (float)xs), ddy = fmaf(dy, 20.0f, (float)ys);
+					normalize2(ddx, ddy);
+					int nx = (short)(int)fmaf(rf, ddx, pxf), ny = (short)(int)fmaf(rf, ddy, pyf);
+					if (nx < 6 || ny < 6 || nx >= W - 6 || ny >= H - 6) continue;
+					int nc = nx + ny * W;
+					if (a.states[nc] != APD_STRONG) {
+						const short2 s = a.nearest[nc];
+						if (s.x == -1 || s.y == -1) continue;
+						nx = s.x; ny = s.y;
+					}
+					float tdx = (float)(nx - px), tdy = (float)(ny - py);
+					normalize2(tdx, tdy);
+					const float cosv = fmaf(tdx, dx, tdy * dy);
+					if (cosv > ac.thresh) { sp[di] = make_short2((short)nx, (short)ny); valid |= 1u << di; ++found; break; }
+				}
+				if ((valid >> di) & 1u) break;
+			}
+			const float rx = fmaf(dx, ac.cos_a, -(dy * ac.sin_a)), ry = fmaf(dx, ac.sin_a, dy * ac.cos_a);
+			dx = rx; dy = ry;
+			normalize2(dx, dy);
+		}
+	}
+	if (found <= 3) { a.reliable[center] = 0; rng_store(a.rng, center, rng); return; }
+
+	short2 pts[32]; float3 p3[32]; int vc = 0;
+	const float3 c3 = point3(rc, px, py, a.planes[center].w);       // planes[].w still holds the prior depth here
+	for (int i = 0; i < 32; ++i) {
+		pts[i] = make_short2(-1, -1);
+		if ((valid >> i) & 1u) {
+			const short2 s = sp[i];
+			pts[vc] = s;
+			p3[vc] = point3(rc, s.x, s.y, a.planes[s.x + s.y * W].w);
+			++vc;
+		}
+	}
+	const float inv_dd = rcpf(a.depth_max - a.depth_min);
+	float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+	int ua = -1, ub = -1, uc = -1, max_count = 3; bool has = false; float min_cost = FLT_MAX;
+	for (int it = 0; it < 50; ++it) {
+		const int ia = (int)(rng_next(rng) % (unsigned)vc), ib = (int)(rng_next(rng) % (unsigned)vc), ic = (int)(rng_next(rng) % (unsigned)vc);
+		if (ia == ib || ib == ic || ia == ic) continue;
+		if (!point_in_triangle(pts[ia], pts[ib], pts[ic], px, py)) continue;
+		float4 pl;
+		if (!plane_from_points(p3[ia], p3[ib], p3[ic], pl)) continue;
+		int cnt = 0;
+		for (int s = 0; s < vc; ++s) if (plane_dist(pl, p3[s]) * inv_dd < a.ransac_threshold) ++cnt;
+		if (cnt < 6) continue;
+		if (cnt > max_count) {
+			max_count = cnt; min_cost = plane_dist(pl, c3); best = pl; has = true; ua = ia; ub = ib; uc = ic;
+		} else if (cnt == max_count) {
+			const float cd = plane_dist(pl, c3);
+			if (cd < min_cost) { min_cost = cd; best = pl; ua = ia; ub = ib; uc = ic; }
+		}
+	}
+	rng_store(a.rng, center, rng);
+	if (!has) { a.reliable[center] = 0; return; }
+	float wgt[32];
+	for (int i = 0; i < vc; ++i) {
+		float d = plane_dist(best, p3[i]);
+		if (d * inv_dd >= a.ransac_threshold) { pts[i] = make_short2(-1, -1); wgt[i] = FLT_MAX; continue; }
+		if (i == ua || i == ub || i == uc) d -= 1.0f;
+		wgt[i] = d;
+	}
+	for (int i = 1; i < vc; ++i) {   // sort_small_weighted, APD.cu:14-27
+		const short2 tp = pts[i]; const float tw = wgt[i]; int j = i;
+		for (; j >= 1 && tw < wgt[j - 1]; --j) { pts[j] = pts[j - 1]; wgt[j] = wgt[j - 1]; }
+		pts[j] = tp; wgt[j] = tw;
+	}
+	for (int k = 1; k < APD_NEIGHBOUR_NUM; ++k) a.anchors[(size_t)k * n + center] = pts[k - 1];
+	a.reliable[center] = 1;
+}
+
+// K4
+__global__ void k_demote_unreliable(const Args a) {
+	const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+	if (px >= a.W || py >= a.H) return;
+	const size_t c = (size_t)py * a.W + px;
+	if (a.states[c] == APD_WEAK && a.reliable[c] != 1) a.states[c] = APD_UNKNOWN;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8
+__global__ void __launch_bounds__(128) k_fit_plane(const Args a) {
+	const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+	if (px >= a.W || py >= a.H) return;
+	const int W = a.W; const size_t n = (size_t)W * a.H;
+	const int center = py * W + px;
+	if (a.states[center] != APD_WEAK) { a.fit_planes[center] = a.planes[center]; return; }
+	const RefConst rc = *a.ref;
+	short2 pts[8]; float3 p3[8]; int cnt = 0;
+	for (int k = 1; k < APD_NEIGHBOUR_NUM; ++k) {
+		const short2 s = a.anchors[(size_t)k * n + center];
+		if (s.x == -1 || s.y == -1) continue;
+		const float depth = plane_depth(rc, a.planes[s.x + s.y * W], (float)s.x, (float)s.y);
+		pts[cnt] = s; p3[cnt] = point3(rc, s.x, s.y, depth); ++cnt;
+	}
+	if (cnt < 3) { a.fit_planes[center] = a.planes[center]; return; }
+	Rng rng = rng_load(a.rng, center);
+	float min_cost = FLT_MAX; float4 best = make_float4(0.f, 0.f, 0.f, 0.f); bool has = false;
+	for (int it = 0; it < 50; ++it) {
+		const int ia = (int)(rng_next(rng) % (unsigned)cnt), ib = (int)(rng_next(rng) % (unsigned)cnt), ic = (int)(rng_next(rng) % (unsigned)cnt);
+		if (ia == ib || ib == ic || ia == ic) continue;
+		if (!point_in_triangle(pts[ia], pts[ib], pts[ic], px, py)) continue;
+		float4 pl;
+		if (!plane_from_points(p3[ia], p3[ib], p3[ic], pl)) continue;
+		float cost = 0.0f;
+		for (int s = 0; s < cnt; ++s) { if (s == ia || s == ib || s == ic) continue; cost += plane_dist(pl, p3[s]); }
+		if (cost < min_cost) { min_cost = cost; best = pl; has = true; }
+		if (min_cost == 0.0f) break;
+	}
+	rng_store(a.rng, center, rng);
+	if (has) {
+		const float xf = (float)px, yf = (float)py;
+		const float depth = plane_depth(rc, a.planes[center], xf, yf);
+		float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
+		float n2 = X1 * X1; n2 = fmaf(X0, X0, n2); n2 = fmaf(depth, depth, n2);
+		const float rn = rcpf(sqrtaf(n2));
+		float dot = (X1 * rn) * best.y; dot = fmaf(X0 * rn, best.x, dot); dot = fmaf(depth * rn, best.z, dot);
+		if (dot > 0.0f) best = make_float4(-best.x, -best.y, -best.z, -best.w);
+		a.fit_planes[center] = best;
+	} else {
+		a.fit_planes[center] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// ComputeBilateralNCCNew, APD.cu:400-528: patch k = 0 is the pixel's own 6x6 window, patches 1..8 are 3x3
+// windows (offsets {-5,0,5}) centred on the deformable anchors, all warped by the same homography.
+template <int INC>
+__device__ __forceinline__ float ncc_window(const Args &a, int layer, const float *h, int cx, int cy, float inv_w) {
+	NccSums t = {0.f, 0.f, 0.f, 0.f, 0.f};
+	const float *base = a.ref_pad + (size_t)(cy + kRefPad) * a.ref_pitch + (cx + kRefPad);
+#pragma unroll
+	for (int i = -5; i <= 5; i += INC) {
+		const float xf = (float)(cx + i);
+		const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
+		NccSums r = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+		for (int j = -5; j <= 5; j += INC) {
+			const float rp = __ldg(base + (ptrdiff_t)j * a.ref_pitch + i);
+			const float sp = src_tap(a.img_tex, layer, h, ax, ay, az, (float)(cy + j));
+			r.r += rp; r.rr = fmaf(rp, rp, r.rr); r.rs = fmaf(rp, sp, r.rs);
+			r.s += sp; r.ss = fmaf(sp, sp, r.ss);
+		}
+		t.r += r.r; t.rr += r.rr; t.s += r.s; t.ss += r.ss; t.rs += r.rs;
+	}
+	return ncc_cost(t, inv_w);
+}
+
+struct Anchors { short2 p[APD_NEIGHBOUR_NUM]; };
+
+__device__ float ncc_deform(const Args &a, const RefConst &rc, const ViewConst &vc, int v, const float4 pl,
+                            const Anchors &an, int px, int py, float inv36, float inv9) {
+	const Homog Hm = make_homography(rc, vc, pl);
+	if (!centre_inside(Hm, vc, (float)px, (float)py)) return kCostMax;
+	const float *h = Hm.h;
+	const float Wf = (float)a.W, Hf = (float)a.H;
+	float center_cost = 0.0f, strong_cost = 0.0f; int cnt = 0;
+#pragma unroll 1
+	for (int k = 0; k < APD_NEIGHBOUR_NUM; ++k) {
+		const short2 q = an.p[k];
+		if (q.x == -1 || q.y == -1) continue;
+		const float xf = (float)q.x, yf = (float)q.y;
+		const float rz = rcpf(h[8] + fmaf(h[6], xf, h[7] * yf));
+		const float sx = (h[2] + fmaf(h[0], xf, h[1] * yf)) * rz;
+		const float sy = (h[5] + fmaf(h[3], xf, h[4] * yf)) * rz;
+		if (sx < 0.0f || sy < 0.0f || sx >= Wf || sy >= Hf) {
+			if (k == 0) return kCostMax;
+			if ((a.sel_views[q.x + q.y * a.W] >> v) & 1u) { strong_cost += kCostMax; ++cnt; }
+			continue;
+		}
+		if (k == 0) center_cost = ncc_window<2>(a, v + 1, h, q.x, q.y, inv36);
+		else { strong_cost += ncc_window<5>(a, v + 1, h, q.x, q.y, inv9); ++cnt; }
+	}
+	if (cnt == 0) return center_cost;
+	strong_cost = strong_cost * rcpf((float)cnt);
+	strong_cost = (strong_cost > kCostMax) ? kCostMax : strong_cost;      // OpenCV MIN(strong_cost, cost_max)
+	return (float)fma((double)center_cost, 0.25, (double)strong_cost * 0.75);
+}
+
+// geometric term, shared with the strong TU (defined there as a __device__ inline in the header would
+// duplicate code; it is small, so it is restated here from APD.cu:752-789 with the same operations)
+__device__ __forceinline__ float geom_cost_w(const Args &a, const RefConst &rc, const ViewConst &vc, int layer, const float4 pl, float xf, float yf) {
+	const float depth = plane_depth(rc, pl, xf, yf);
+	float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
+	const float *R = rc.cam.R;
+	float Px = rc.cam.c[0] + fmaf(R[6], depth, fmaf(R[0], X0, R[3] * X1));
+	float Py = rc.cam.c[1] + fmaf(R[7], depth, fmaf(R[1], X0, R[4] * X1));
+	float Pz = rc.cam.c[2] + fmaf(R[8], depth, fmaf(R[2], X0, R[5] * X1));
+	const apd_camera &s = vc.cam;
+	float tx = s.t[0] + fmaf(s.R[2], Pz, fmaf(s.R[0], Px, s.R[1] * Py));
+	float ty = s.t[1] + fmaf(s.R[5], Pz, fmaf(s.R[3], Px, s.R[4] * Py));
+	float tz = s.t[2] + fmaf(s.R[8], Pz, fmaf(s.R[6], Px, s.R[7] * Py));
+	float rd = rcpf(fmaf(s.K[8], tz, fmaf(s.K[6], tx, s.K[7] * ty)));
+	float sx = fmaf(s.K[2], tz, fmaf(s.K[0], tx, s.K[1] * ty)) * rd;
+	float sy = fmaf(s.K[5], tz, fmaf(s.K[3], tx, s.K[4] * ty)) * rd;
+	const float sd = tex2DLayered<float>(a.depth_tex, (float)(int)sx + 0.5f, (float)(int)sy + 0.5f, layer);
+	if (sd == 0.0f) return 3.0f;
+	const float rsK0 = rcpf(s.K[0]), rsK4 = rcpf(s.K[4]);
+	float Y0 = (sd * (sx - s.K[2])) * rsK0;
+	float Y1 = (sd * (sy - s.K[5])) * rsK4;
+	float Qx = s.c[0] + fmaf(s.R[6], sd, fmaf(s.R[0], Y0, s.R[3] * Y1));
+	float Qy = s.c[1] + fmaf(s.R[7], sd, fmaf(s.R[1], Y0, s.R[4] * Y1));
+	float Qz = s.c[2] + fmaf(s.R[8], sd, fmaf(s.R[2], Y0, s.R[5] * Y1));
+	const float *K = rc.cam.K; const float *t = rc.cam.t;
+	float ux = t[0] + fmaf(R[2], Qz, fmaf(R[0], Qx, R[1] * Qy));
+	float uy = t[1] + fmaf(R[5], Qz, fmaf(R[3], Qx, R[4] * Qy));
+	float uz = t[2] + fmaf(R[8], Qz, fmaf(R[6], Qx, R[7] * Qy));
+	float rb = rcpf(fmaf(K[8], uz, fmaf(K[6], ux, K[7] * uy)));
+	float dc = fmaf(-fmaf(K[2], uz, fmaf(K[0], ux, K[1] * uy)), rb, xf);
+	float dr = fmaf(-fmaf(K[5], uz, fmaf(K[3], ux, K[4] * uy)), rb, yf);
+	return fminf(sqrtaf(fmaf(dc, dc, dr * dr)), 3.0f);
+}
+
+// weighted cost of one plane for a WEAK pixel over the sampled views:
+//   sum_v w_v * (ncc_deform + geom_factor * geom) (APD.cu:918-927, 960-969, 1464-1471)
+__device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float4 pl, const Anchors &an,
+                           const VW &vw, int px, int py, float inv36, float inv9) {
+	float acc = 0.0f;
+	for (int v = 0; v < a.S; ++v) {
+		const int w = vw_get(vw, v);
+		if (w == 0) continue;
+		float c = ncc_deform(a, rc, sv[v], v, pl, an, px, py, inv36, inv9);
+		if (a.geom) c = fmaf(a.geom_factor, geom_cost_w(a, rc, sv[v], v + 1, pl, (float)px, (float)py), c);
+		acc = fmaf((float)w, c, acc);
+	}
+	return acc;
+}
+
+constexpr int kWeakNT = 128;
+constexpr int kWeakTW = 32, kWeakTH = 8;      // 128 pixels of one colour per block
+
+__global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, const int color) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	RefConst *sr = reinterpret_cast<RefConst *>(smem_raw);
+	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
+	float *cm = reinterpret_cast<float *>(sv + a.S);          // [9*S][NT]
+	const int tid = threadIdx.x;
+	{
+		const int nv = a.S * (int)(sizeof(ViewConst) / 4);
+		const uint32_t *g = reinterpret_cast<const uint32_t *>(a.views); uint32_t *s = reinterpret_cast<uint32_t *>(sv);
+		for (int i = tid; i < nv; i += kWeakNT) s[i] = g[i];
+		const uint32_t *gr = reinterpret_cast<const uint32_t *>(a.ref); uint32_t *srr = reinterpret_cast<uint32_t *>(sr);
+		for (int i = tid; i < (int)(sizeof(RefConst) / 4); i += kWeakNT) srr[i] = gr[i];
+	}
+	__syncthreads();
+	const int lx = tid & 31, row = tid >> 5;                   // 4 row pairs of 32 columns
+	const int px = blockIdx.x * kWeakTW + lx;
+	const int ybase = blockIdx.y * kWeakTH + 2 * row;
+	const int py = ybase + ((px + ybase + color) & 1);
+	if (px >= a.W || py >= a.H || py >= a.half_rows) return;
+	const int W = a.W, S = a.S; const size_t n = (size_t)W * a.H;
+	const int center = py * W + px;
+	if (a.states[center] != APD_WEAK) return;
+	const RefConst &rc = *sr;
+	const float xf = (float)px, yf = (float)py;
+	const float inv36 = a.inv_w[0], inv9 = a.inv_w[1];
+	float *cmt = cm + tid;
+#define CM(k, v) cmt[((k) * S + (v)) * kWeakNT]
+#define PROB(v) cmt[(8 * S + (v)) * kWeakNT]
+	Anchors an;
+	for (int k = 0; k < APD_NEIGHBOUR_NUM; ++k) an.p[k] = a.anchors[(size_t)k * n + center];
+
+	// candidates = current planes of the anchors that are (still) STRONG (APD.cu:1352-1363)
+	unsigned flags = 0u; int pos[8];
+#pragma unroll 1
+	for (int k = 0; k < 8; ++k) {
+		const short2 q = an.p[k + 1];
+		pos[k] = 0;
+		const bool ok = !(q.x == -1 || q.y == -1) && a.states[q.x + q.y * W] == APD_STRONG;
+		if (ok) {
+			flags |= 1u << k; pos[k] = q.x + q.y * W;
+			const float4 pl = a.planes[pos[k]];
+			for (int v = 0; v < S; ++v) CM(k, v) = ncc_deform(a, rc, sv[v], v, pl, an, px, py, inv36, inv9);
+		} else {
+			for (int v = 0; v < S; ++v) CM(k, v) = (k == 0 && v == 0) ? 2.0f : 0.0f;      // `= {2.0f}` quirk, APD.cu:1345
+		}
+	}
+	// view selection (APD.cu:1365-1434): priors from every existing anchor, STRONG or not
+	const float thr = 0.8 * __expf((float)(unsigned)(iter * iter) * -0.011111111380159854889f);
+	const float thr_fallback = __expf((thr * thr) * -3.125f);
+	float prob_sum = 0.0f;
+	for (int v = 0; v < S; ++v) {
+		float prior = 0.0f;
+		for (int k = 1; k < APD_NEIGHBOUR_NUM; ++k) {
+			const short2 q = an.p[k];
+			if (q.x == -1 || q.y == -1) continue;
+			prior += ((a.sel_views[q.x + q.y * W] >> v) & 1u) ? 0.9f : 0.1f;
+		}
+		float count = 0.0f, tmpw = 0.0f; int count_false = 0;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			const float c = CM(k, v);
+			if (c < thr) { tmpw += __expf((c * c) * -5.5555553436279296875f); count += 1.0f; }
+			if (c > 1.2f) count_false++;
+		}
+		float p = 0.0f;
+		if (count > 2.0f && count_false < 3) p = tmpw * rcpf(count);
+		else if (count_false < 3) p = thr_fallback;
+		p = p * prior;
+		PROB(v) = p; prob_sum += p;
+	}
+	Rng rng = rng_load(a.rng, center);
+	VW vw; vw.lo = 0ull; vw.hi = 0ull;
+	{
+		const float inv = rcpf(prob_sum); float cum = 0.0f;
+		for (int v = 0; v < S; ++v) { cum = fmaf(inv, PROB(v), cum); PROB(v) = cum; }
+		for (int s = 0; s < 15; ++s) {
+			const float r = rng_uniform(rng) - 1.1920928955078125e-07f;
+			for (int v = 0; v < S; ++v) if (PROB(v) > r) { vw_add(vw, v); break; }
+		}
+	}
+	uint32_t temp_sel = 0u; float weight_norm = 0.0f;
+	for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) { temp_sel |= 1u << v; weight_norm += (float)w; } }
+	const float inv_wn = rcpf(weight_norm);
+
+	float best_cost; int best_k;
+	{
+		float fc[8];
+		const float miss = a.geom_factor * 3.0f;
+#pragma unroll 1
+		for (int k = 0; k < 8; ++k) {
+			float acc = 0.0f;
+			const bool fl = (flags >> k) & 1u;
+			float4 pl = make_float4(0.f, 0.f, 0.f, 1.f);
+			if (fl) pl = a.planes[pos[k]];
+			for (int v = 0; v < S; ++v) {
+				const int w = vw_get(vw, v);
+				if (w == 0) continue;
+				float c = CM(k, v);
+				if (a.geom) c = fl ? fmaf(a.geom_factor, geom_cost_w(a, rc, sv[v], v + 1, pl, xf, yf), c) : fmaf(a.geom_factor, 3.0f, c);
+				acc = fmaf((float)w, c, acc);
+			}
+			(void)miss;
+			fc[k] = acc * inv_wn;
+		}
+		best_cost = fc[0]; best_k = 0;
+#pragma unroll
+		for (int k = 1; k < 8; ++k) if (fc[k] <= best_cost) { best_cost = fc[k]; best_k = k; }
+	}
+
+	float4 pl_now = a.planes[center];
+	float cost_now = weak_cost(a, rc, sv, pl_now, an, vw, px, py, inv36, inv9) * inv_wn;
+	const float cost_stored = cost_now;
+	float depth_now = plane_depth(rc, pl_now, xf, yf);
+	if ((flags >> best_k) & 1u) {
+		int bp = pos[0];
+#pragma unroll
+		for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
+		const float4 cand = a.planes[bp];
+		const float d = plane_depth(rc, cand, xf, yf);
+		if (d >= a.depth_min && d <= a.depth_max && best_cost < cost_now) {
+			depth_now = d; pl_now = cand; cost_now = best_cost; a.sel_views[center] = temp_sel;
+		}
+	}
+	// PlaneHypothesisRefinementWeak, APD.cu:892-980
+	{
+		const float4 fit = a.fit_planes[center];
+		if (!(fit.x == 0.0f && fit.y == 0.0f && fit.z == 0.0f)) {
+			{
+				const float tc = weak_cost(a, rc, sv, fit, an, vw, px, py, inv36, inv9) * inv_wn;
+				const float d = plane_depth(rc, fit, xf, yf);
+				if (d >= a.depth_min && d <= a.depth_max && tc < cost_now) { depth_now = d; pl_now = fit; cost_now = tc; }
+			}
+			const float depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
+			const float4 n_rand = random_normal(rc, xf, yf, rng, depth_now);
+			const float lo = depth_now * (1.0f - 0.02f);
+			const float span = fmaf(depth_now, 1.0f + 0.02f, -lo);
+			const float depth_pert = fmaf(span, rng_uniform(rng), lo);
+			const float4 n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
+			const float4 n0 = pl_now; const float d0 = depth_now;
+#pragma unroll 1
+			for (int i = 0; i < 5; ++i) {
+				const float di = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : d0);
+				float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
+				t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
+				const float tc = weak_cost(a, rc, sv, t, an, vw, px, py, inv36, inv9) * inv_wn;
+				const float d = plane_depth(rc, t, xf, yf);
+				if (d >= a.depth_min && d <= a.depth_max && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+			}
+		}
+	}
+	rng_store(a.rng, center, rng);
+	vw_store(a.view_w, center, vw);
+	float4 final_plane = a.planes[center];
+	if (a.state == APD_REFINE_INIT) {
+		if ((double)cost_now < (double)cost_stored - 0.1) { final_plane = pl_now; a.planes[center] = pl_now; }
+	} else { final_plane = pl_now; a.planes[center] = pl_now; }
+	{   // "update cost with old method" (APD.cu:1499-1507): plain NCC of the committed plane
+		float acc = 0.0f;
+		for (int v = 0; v < S; ++v) {
+			const int w = vw_get(vw, v);
+			if (w == 0) continue;
+			const Homog Hm = make_homography(rc, sv[v], final_plane);
+			float c = kCostMax;
+			if (centre_inside(Hm, sv[v], xf, yf)) c = ncc_window<2>(a, v + 1, Hm.h, px, py, inv36);
+			acc = fmaf((float)w, c, acc);
+		}
+		a.costs[center] = acc * inv_wn;
+	}
+#undef CM
+#undef PROB
+}
+
+// ------------------------------------------------------------------------------------------------
+static int8_t *g_dummy = nullptr;
+cudaError_t launch_nearest_strong(cudaStream_t st, const Args &a) {
+	// row scratch: reuse the fit-plane buffer (16 B/px, rewritten by K8 before any use)
+	int8_t *rowdx = reinterpret_cast<int8_t *>(a.fit_planes);
+	dim3 b(32, 8), g((a.W + 31) / 32, (a.H + 7) / 8);
+	k_row_nearest<<<g, b, 0, st>>>(a.states, a.W, a.H, rowdx);
+	k_nearest_strong<<<g, b, 0, st>>>(a, rowdx);
+	(void)g_dummy;
+	return cudaGetLastError();
+}
+static AnchorConsts *g_ac[16] = {nullptr};
+cudaError_t launch_gen_anchors(cudaStream_t st, const Args &a) {
+	int dev = 0; cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
+	if (!g_ac[dev]) { cudaError_t e = cudaMalloc((void **)&g_ac[dev], 4 * sizeof(AnchorConsts)); if (e != cudaSuccess) return e; }
+	AnchorConsts *ac = g_ac[dev] + (a.rotate_time == 1 ? 0 : a.rotate_time == 2 ? 1 : 2);
+	launch_anchor_consts(st, a.rotate_time, ac);
+	dim3 b(32, 4), g((a.W + 31) / 32, (a.H + 3) / 4);
+	k_gen_anchors<<<g, b, 0, st>>>(a, ac);
+	return cudaGetLastError();
+}
+cudaError_t launch_demote_unreliable(cudaStream_t st, const Args &a) {
+	dim3 b(32, 8), g((a.W + 31) / 32, (a.H + 7) / 8);
+	k_demote_unreliable<<<g, b, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_fit_plane(cudaStream_t st, const Args &a) {
+	dim3 b(32, 4), g((a.W + 31) / 32, (a.H + 3) / 4);
+	k_fit_plane<<<g, b, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_weak(cudaStream_t st, const Args &a, int iter, int color) {
+	const size_t smem = sizeof(RefConst) + (size_t)a.S * sizeof(ViewConst) + (size_t)9 * a.S * kWeakNT * 4;
+	if (smem > 227 * 1024) return cudaErrorInvalidValue;
+	cudaFuncSetAttribute(k_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	dim3 g((a.W + kWeakTW - 1) / kWeakTW, (a.H + kWeakTH - 1) / kWeakTH);
+	k_weak<<<g, kWeakNT, smem, st>>>(a, iter, color);
+	return cudaGetLastError();
+}
+
+}  // namespace apd

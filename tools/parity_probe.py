@@ -23,6 +23,16 @@ def run_case(name, W, H, S, iters, stages="all", **kw):
         d = T.diff_state(T.product_state(apd), ref.get(s))
         rows.append({"stage": s, "name": names[s], **d})
         print(f"[{name}] stage {s:2d} {names[s]:22s} " + " ".join(f"{k}={v:.6f}" for k, v in d.items()), flush=True)
+    if case["params"].use_APD:
+        apd.RunPatchMatch(stage_end=3)
+        anchors, nearest, reliable, fit = apd.GetAnchors()
+        comp, nmap, rnear, rrel, rfit, wc = ref.anchors()
+        weak = case["states"] == 0
+        ra = comp[nmap[weak]]
+        ma = anchors[weak]
+        print(f"[{name}] weak px {weak.sum()} anchors mismatch frac {np.mean((ra != ma).any(axis=(1, 2))):.6f} nearest mismatch {np.mean((rnear[weak] != nearest[weak]).any(-1)):.6f} reliable mismatch {np.mean(rrel[weak] != reliable[weak]):.6f}", flush=True)
+        bad = np.where((ra != ma).any(axis=(1, 2)))[0][:3]
+        for b in bad: print("  ref", ra[b].tolist(), "mine", ma[b].tolist())
     apd.RunPatchMatch()
     mine = T.product_state(apd)
     rp, rs, rv = ref.outputs()
