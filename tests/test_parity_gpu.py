@@ -23,7 +23,8 @@ def bits(a):
     return a.view(np.uint32) if a.dtype == np.float32 else a
 
 
-GOLDEN = ["strong_first_64x48_s2", "strong_geom_64x48_s3", "strong_refineinit_48x40_s2", "smoke_128x96"]
+GOLDEN = ["strong_first_64x48_s2", "strong_geom_64x48_s3", "strong_refineinit_48x40_s2", "smoke_128x96",
+          "apd_geom_96x72_s3", "apd_init_96x72_s3_rot2"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -56,6 +57,11 @@ CASES = [
     dict(W=320, H=240, S=4, iters=1, state=E.REFINE_INIT),
     dict(W=320, H=240, S=4, iters=2, state=E.REFINE_ITER, geom=True),
     dict(W=128, H=96, S=5, iters=1, top_k=2),
+    # adaptive patch deformation ON (WEAK pixels on the textureless rectangles): K2/K3/K4/K8/K9/K10
+    dict(W=320, H=240, S=4, iters=2, state=E.REFINE_ITER, geom=True, use_apd=True),
+    dict(W=320, H=240, S=4, iters=1, state=E.REFINE_INIT, use_apd=True, rotate_time=2, ransac_threshold=0.00875, weak_peak_radius=6),
+    dict(W=203, H=157, S=6, iters=1, state=E.REFINE_ITER, use_apd=True, rotate_time=1, ransac_threshold=0.01),
+    dict(W=256, H=192, S=3, iters=3, state=E.REFINE_ITER, geom=True, use_apd=True, rotate_time=4, ransac_threshold=0.00625),
 ]
 
 
@@ -74,6 +80,14 @@ def test_live_reference_bit_exact(kw):
         apd.RunPatchMatch(stage_end=s)
         d = T.diff_state(T.product_state(apd), ref.get(s))
         assert max(d.values()) == 0.0, f"stage {s}: {d}"
+    if case["params"].use_APD:
+        apd.RunPatchMatch(stage_end=3)
+        anchors, nearest, reliable, _ = apd.GetAnchors()
+        comp, nmap, rnear, rrel, _, wc = ref.anchors()
+        weak = case["states"] == 0
+        assert wc == int(weak.sum()) and wc > 100
+        assert np.array_equal(anchors[weak], comp[nmap[weak]])          # deformable anchors, all 9 slots
+        assert np.array_equal(nearest[weak], rnear[weak]) and np.array_equal(reliable[weak], rrel[weak])
     apd.RunPatchMatch()
     rp, rs, rv = ref.outputs()
     assert np.array_equal(bits(apd.GetPlaneHypotheses()), bits(rp))

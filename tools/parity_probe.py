@@ -81,6 +81,10 @@ if "apd" in which:
     run_case("apd refine_init 320x240 S4 rot2", 320, 240, 4, 1, state=E.REFINE_INIT, use_apd=True, rotate_time=2, ransac_threshold=0.00875, weak_peak_radius=6)
 if "time" in which:
     time_case("time 1024x768 S9 it3", 1024, 768, 9, 3)
+if "cfg3" in which:
+    time_case("cfg3 6221x4146 S9 apd+geom it3", 6221, 4146, 9, 3, reps=1, state=E.REFINE_ITER, geom=True, use_apd=True)
+if "cfg3s" in which:
+    time_case("cfg3-small 1555x1036 S9 apd+geom it3", 1555, 1036, 9, 3, reps=2, state=E.REFINE_ITER, geom=True, use_apd=True)
 if "cfg2" in which:
     time_case("cfg2 3111x2074 S9 it3", 3111, 2074, 9, 3, reps=2)
 json.dump(out, open("gpurun_out/parity_probe.json", "w"), indent=1)
