@@ -244,6 +244,92 @@ __device__ __forceinline__ float ncc_strong(cudaTextureObject_t tex, int layer, 
 	return ncc_cost(t, inv_w);
 }
 
+// ---- quad-cooperative NCC ------------------------------------------------------------------------
+// Measured on B200 (tools/tex_probe3.cu, profiles/): the texture data pipe delivers the full
+// 4 bilinear fetches/clk/SM only when the four lanes of a quad touch a compact (<= ~4x4 texel)
+// footprint; four lanes sampling four unrelated places (= four different plane hypotheses, the
+// natural thread-per-pixel mapping) run at ~35 %. So the four lanes of a quad fetch TOGETHER:
+// evaluation e (owned by lane e of the quad: its homography, pixel and view) is fetched by all four
+// lanes, lane s taking the 3x3 taps of quadrant s ^ e of the 6x6 window (taps (2c+a, 2d+b)), so every
+// TEX instruction covers a 2x2 cluster of neighbouring taps. The warped source patch is staged in
+// shared memory (one [36 taps][32 lanes] slab per warp) and each lane then accumulates its OWN
+// evaluation's 36 taps from there in the reference's order (x-offset outer, y-offset inner, row
+// sums) -- bit-identical sums. Slab addressing: tap T of evaluation e of quad Q sits at
+// T*32 + Q*4 + (e ^ quadrant(T)); writers therefore store at T*32 + lane and readers load from
+// T*32 + (lane ^ quadrant(T)): both conflict-free.
+// All four lanes of a quad must call this convergently; `want` = false lanes only help.
+constexpr int kPatchFloats = 36 * 32;            // per warp
+struct QuadCtx { float *slab; unsigned qmask; int lane, ql; };
+__device__ __forceinline__ QuadCtx make_quad_ctx(float *patch_base, int tid) {
+	QuadCtx q; q.slab = patch_base + (tid >> 5) * kPatchFloats; q.lane = tid & 31; q.ql = tid & 3; q.qmask = 0xFu << (q.lane & ~3);
+	return q;
+}
+
+__device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc, bool want,
+                                           const float *tile, int pitch, int lx, int ly, int px, int py, float inv_w) {
+	// must be called by all 32 lanes of the warp convergently
+	const bool active = want && centre_inside(Hm, vc, (float)px, (float)py);
+	const unsigned ballot = __ballot_sync(0xffffffffu, active);
+	const unsigned my_quad = (ballot >> (q.lane & ~3)) & 0xFu;      // which of my quad's four evaluation slots are live
+	float v[4][9];
+	// phase 1: all 36 fetches of the four evaluations are issued before any result is consumed
+#pragma unroll
+	for (int e = 0; e < 4; ++e) {
+		if ((ballot & (0x11111111u << e)) == 0u) continue;            // warp-uniform: nobody owns a live slot e
+		float h[9];
+#pragma unroll
+		for (int i = 0; i < 9; ++i) h[i] = __shfl_sync(0xffffffffu, Hm.h[i], e, 4);
+		const int pxe = __shfl_sync(0xffffffffu, px, e, 4), pye = __shfl_sync(0xffffffffu, py, e, 4), lay = __shfl_sync(0xffffffffu, layer, e, 4);
+		if ((my_quad >> e) & 1u) {
+			const int qd = q.ql ^ e;
+			const int x0 = pxe - 5 + 2 * (qd & 1), y0 = pye - 5 + 2 * (qd >> 1);
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				const float xf = (float)(x0 + 4 * c);
+				const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
+#pragma unroll
+				for (int d = 0; d < 3; ++d) v[e][c * 3 + d] = src_tap(tex, lay, h, ax, ay, az, (float)(y0 + 4 * d));
+			}
+		}
+	}
+	// phase 2: stage the warped patches: tap (2c+qa, 2d+qb) -> T = 12c + 2d + 6qa + qb, slot T*32 + lane
+#pragma unroll
+	for (int e = 0; e < 4; ++e) {
+		if ((my_quad >> e) & 1u) {
+			const int qd = q.ql ^ e;
+			float *dst = q.slab + (6 * (qd & 1) + (qd >> 1)) * 32 + q.lane;
+#pragma unroll
+			for (int c = 0; c < 3; ++c)
+#pragma unroll
+				for (int d = 0; d < 3; ++d) dst[(12 * c + 2 * d) * 32] = v[e][c * 3 + d];
+		}
+	}
+	__syncwarp();
+	float cost = kCostMax;
+	if (active) {
+		NccSums t = {0.f, 0.f, 0.f, 0.f, 0.f};
+		const float *base = tile + (ly + kHalo) * pitch + (lx + kHalo);
+		const float *s0 = q.slab + q.lane, *s1 = q.slab + (q.lane ^ 1), *s2 = q.slab + (q.lane ^ 2), *s3 = q.slab + (q.lane ^ 3);
+#pragma unroll
+		for (int i = 0; i < 6; ++i) {
+			NccSums r = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+			for (int j = 0; j < 6; ++j) {
+				const float rp = base[(2 * j - 5) * pitch + (2 * i - 5)];
+				const int quad = (i & 1) + 2 * (j & 1);
+				const float *sq = quad == 0 ? s0 : quad == 1 ? s1 : quad == 2 ? s2 : s3;
+				const float sp = sq[(i * 6 + j) * 32];
+				r.r += rp; r.rr = fmaf(rp, rp, r.rr); r.rs = fmaf(rp, sp, r.rs);
+				r.s += sp; r.ss = fmaf(sp, sp, r.ss);
+			}
+			t.r += r.r; t.rr += r.rr; t.s += r.s; t.ss += r.ss; t.rs += r.rs;
+		}
+		cost = ncc_cost(t, inv_w);
+	}
+	__syncwarp();
+	return cost;
+}
+
 // ---- kernel arguments -------------------------------------------------------------------------------
 struct Args {
 	int W, H, S;                 // S = number of source views = num_images - 1
@@ -262,6 +348,7 @@ struct Args {
 	uint32_t *sel_views; uint8_t *states; uint2 *rng; uint4 *view_w;
 	short2 *anchors;             // [9][W*H]: slot k of pixel p at anchors[k*W*H + p] (reference: compact [weak_idx*9+k])
 	short2 *nearest; uint8_t *reliable;
+	float *scratch;              // per-block cost matrices of the propagation kernels (9*S floats per pixel of one colour)
 };
 
 // view weights: 32 nibbles (sum <= 15) in one uint4 per pixel (reference: 32 bytes, APD.cpp:645)

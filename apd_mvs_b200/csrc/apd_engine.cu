@@ -48,6 +48,7 @@ struct apd_engine {
 	uint8_t *states = nullptr, *prior_states = nullptr, *reliable = nullptr;
 	uint2 *rng = nullptr; uint4 *view_w = nullptr;
 	short2 *anchors = nullptr, *nearest = nullptr;
+	float *scratch = nullptr;
 	bool have_images = false, have_cams = false, have_depths = false, have_planes = false, have_states = false;
 	std::vector<cudaEvent_t> events;
 	std::vector<float> stage_ms;
@@ -125,6 +126,10 @@ extern "C" int apd_create(apd_handle *out, int device, int width, int height, in
 	ALLOC(h->states, n); ALLOC(h->prior_states, n); ALLOC(h->reliable, n);
 	ALLOC(h->rng, n * 24); ALLOC(h->view_w, n * 16);
 	ALLOC(h->anchors, n * APD_NEIGHBOUR_NUM * sizeof(short2)); ALLOC(h->nearest, n * sizeof(short2));
+	{   // one [9*S][128] slab per 32x8 tile of the half-resolution launches
+		const size_t tiles = (size_t)((width + 31) / 32) * ((height + 7) / 8);
+		ALLOC(h->scratch, tiles * 9 * (size_t)h->S * 128 * 4);
+	}
 #undef ALLOC
 	if (make_layered(h, &h->img_arr, &h->img_tex) != APD_OK) return bail(APD_E_CUDA);
 	cudaMemsetAsync(h->costs, 0, n * 4, h->stream);
@@ -147,7 +152,7 @@ extern "C" void apd_destroy(apd_handle h) {
 	if (h->img_arr) cudaFreeArray(h->img_arr);
 	if (h->depth_arr) cudaFreeArray(h->depth_arr);
 	void *ptrs[] = {h->ref_lin, h->ref_pad, h->d_cams, h->d_views, h->d_ref, h->d_invw, h->planes, h->fit_planes, h->prior_planes,
-	                h->costs, h->sel_views, h->prior_views, h->states, h->prior_states, h->reliable, h->rng, h->view_w, h->anchors, h->nearest};
+	                h->costs, h->sel_views, h->prior_views, h->states, h->prior_states, h->reliable, h->rng, h->view_w, h->anchors, h->nearest, h->scratch};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
@@ -267,7 +272,7 @@ static Args make_args(apd_handle h) {
 	a.ref_pad = h->ref_pad; a.views = h->d_views; a.ref = h->d_ref;
 	a.planes = h->planes; a.fit_planes = h->fit_planes; a.costs = h->costs;
 	a.sel_views = h->sel_views; a.states = h->states; a.rng = h->rng; a.view_w = h->view_w;
-	a.anchors = h->anchors; a.nearest = h->nearest; a.reliable = h->reliable;
+	a.anchors = h->anchors; a.nearest = h->nearest; a.reliable = h->reliable; a.scratch = h->scratch;
 	return a;
 }
 

@@ -99,7 +99,9 @@ __global__ void k_rng_seed(uint2 *rng, int W, int H, unsigned long long seed) {
 // Shared-memory staging of the reference tile (+5 px halo) and of the per-view constants.
 template <int TW, int TH>
 struct TileCfg {
-	static constexpr int PW = ((TW + 2 * kHalo + 3) / 4) * 4;   // row pitch, multiple of 16 B
+	// row pitch: multiple of 16 B and = 8 (mod 16) floats, which makes the reference-window reads of a
+	// warp (16x4 pixels, one colour, rows of alternating parity) bank-conflict free
+	static constexpr int PW = ((TW + 2 * kHalo + 7) / 16) * 16 + 8;
 	static constexpr int PH = TH + 2 * kHalo;
 	static constexpr int ELEMS = PW * PH;
 };
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(kFullNT) k_init_planes(const Args a) {
 // ------------------------------------------------------------------------------------------------
 // K6/K7. One colour of the checkerboard per launch; a block owns a 32x16 pixel tile (256 pixels of
 // that colour); a warp covers a 16x4 patch so that its texture footprint stays compact.
-constexpr int kHalfTW = 32, kHalfTH = 16;
+constexpr int kHalfTW = 32, kHalfTH = 8;      // 128 pixels of one colour per block (4 warps of 16x4)
 
 __device__ __forceinline__ void half_pixel(int tid, int x0, int y0, int color, int &px, int &py, int &lx, int &ly) {
 	// Lanes 4q..4q+3 (one texture quad) own the four same-colour pixels of a 4x2 block, a diamond
@@ -242,24 +244,27 @@ __device__ __forceinline__ void arm_try(ArmMin &m, const float *costs, int pos) 
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_strong(const Args a, const int iter, const int color) {
+__global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, const int color) {
 	using C = TileCfg<kHalfTW, kHalfTH>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float *tile = reinterpret_cast<float *>(smem_raw);
-	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
+	float *xchg = tile + C::ELEMS;                              // [NT/32][36][32] warped source patches
+	RefConst *sr = reinterpret_cast<RefConst *>(xchg + (NT / 32) * kPatchFloats);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
-	float *cm = reinterpret_cast<float *>(sv + a.S);          // [9*S][NT]: 8xS cost matrix + S probabilities
 	const int tid = threadIdx.x;
+	// [9*S][NT] per block: 8xS cost matrix + S probabilities, in a global scratch slab that stays in L1/L2
+	float *cm = a.scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (9 * a.S * NT);
 	const int x0 = blockIdx.x * kHalfTW, y0 = blockIdx.y * kHalfTH;
 	load_tile<kHalfTW, kHalfTH, NT>(a, tile, x0, y0, tid);
 	load_views(a, sv, sr, tid, NT);
 	__syncthreads();
+	const QuadCtx qc = make_quad_ctx(xchg, tid);
 	int px, py, lx, ly;
 	half_pixel(tid, x0, y0, color, px, py, lx, ly);
-	if (px >= a.W || py >= a.H || py >= a.half_rows) return;
 	const int W = a.W, H = a.H, S = a.S;
 	const int center = py * W + px;
-	if (a.states[center] == APD_WEAK) return;
+	// threads without a pixel to update stay: their lanes still fetch for the other lanes of their quad
+	const bool alive = px < W && py < H && py < a.half_rows && a.states[center] != APD_WEAK;
 	const RefConst &rc = *sr;
 	const float xf = (float)px, yf = (float)py;
 	const float inv36 = a.inv_w[0];
@@ -267,11 +272,14 @@ __global__ void __launch_bounds__(NT) k_strong(const Args a, const int iter, con
 	float *cmt = cm + tid;
 #define CM(k, v) cmt[((k) * S + (v)) * NT]
 #define PROB(v) cmt[(8 * S + (v)) * NT]
+#define NCC(v, plane, want) ncc6_quad(qc, a.img_tex, (v) + 1, make_homography(rc, sv[v], plane), sv[v], want, tile, C::PW, lx, ly, px, py, inv36)
 
 	// ---- adaptive checkerboard sampling: 8 candidates (0 up_near 1 up_far 2 down_near 3 down_far
 	//      4 left_near 5 left_far 6 right_near 7 right_far)
 	int pos[8]; unsigned flags = 0u;
-	{
+#pragma unroll
+	for (int k = 0; k < 8; ++k) pos[k] = 0;
+	if (alive) {
 		ArmMin m;
 		if (py > 2) { flags |= 2u; m.pos = center - 3 * W; m.c = costs[m.pos];
 			for (int i = 1; i < 11; ++i) if (py > 2 + 2 * i) arm_try(m, costs, center - 3 * W - 2 * i * W);
@@ -315,67 +323,65 @@ __global__ void __launch_bounds__(NT) k_strong(const Args a, const int iter, con
 	//      row: `float cost_array[8][32] = {2.0f}` sets [0][0] only (APD.cu:1004)
 #pragma unroll 1
 	for (int k = 0; k < 8; ++k) {
-		if ((flags >> k) & 1u) {
-			const float4 pl = a.planes[pos[k]];
+		const bool fl = (flags >> k) & 1u;
+		float4 pl = make_float4(0.f, 0.f, 1.f, 1.f);
+		if (fl) pl = a.planes[pos[k]];
 #pragma unroll 1
-			for (int v = 0; v < S; ++v) {
-				const Homog Hm = make_homography(rc, sv[v], pl);
-				CM(k, v) = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, lx, ly, px, py, inv36);
-			}
-		} else {
-			for (int v = 0; v < S; ++v) CM(k, v) = (k == 0 && v == 0) ? 2.0f : 0.0f;
+		for (int v = 0; v < S; ++v) {
+			const float c = NCC(v, pl, fl);
+			CM(k, v) = fl ? c : ((k == 0 && v == 0) ? 2.0f : 0.0f);
 		}
 	}
 
 	// ---- multi-hypothesis joint view selection, APD.cu:1203-1259
-	const float thr = 0.8 * __expf((float)(unsigned)(iter * iter) * -0.011111111380159854889f);
-	const float thr_fallback = __expf((thr * thr) * -3.125f);
-	uint32_t nb_bits[4]; unsigned nb_ok = 0u;
-	{
-		const int nb_pos[4] = {center - W, center + W, center - 1, center + 1};
+	Rng rng; VW vw; vw.lo = 0ull; vw.hi = 0ull;
+	uint32_t temp_sel = 0u; float inv_wn = 0.0f;
+	float best_cost = 0.0f; int best_k = 0;
+	if (alive) {
+		const float thr = 0.8 * __expf((float)(unsigned)(iter * iter) * -0.011111111380159854889f);
+		const float thr_fallback = __expf((thr * thr) * -3.125f);
+		uint32_t nb_bits[4]; unsigned nb_ok = 0u;
+		{
+			const int nb_pos[4] = {center - W, center + W, center - 1, center + 1};
 #pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			nb_bits[i] = 0u;
-			if ((flags >> (2 * i)) & 1u) { nb_ok |= 1u << i; nb_bits[i] = a.sel_views[nb_pos[i]]; }
+			for (int i = 0; i < 4; ++i) {
+				nb_bits[i] = 0u;
+				if ((flags >> (2 * i)) & 1u) { nb_ok |= 1u << i; nb_bits[i] = a.sel_views[nb_pos[i]]; }
+			}
 		}
-	}
-	float prob_sum = 0.0f;
-	for (int v = 0; v < S; ++v) {
-		float prior = 0.0f;
+		float prob_sum = 0.0f;
+		for (int v = 0; v < S; ++v) {
+			float prior = 0.0f;
 #pragma unroll
-		for (int i = 0; i < 4; ++i)
-			if ((nb_ok >> i) & 1u) prior += ((nb_bits[i] >> v) & 1u) ? 0.9f : 0.1f;
-		float count = 0.0f, tmpw = 0.0f; int count_false = 0;
+			for (int i = 0; i < 4; ++i)
+				if ((nb_ok >> i) & 1u) prior += ((nb_bits[i] >> v) & 1u) ? 0.9f : 0.1f;
+			float count = 0.0f, tmpw = 0.0f; int count_false = 0;
 #pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			const float c = CM(k, v);
-			if (c < thr) { tmpw += __expf((c * c) * -5.5555553436279296875f); count += 1.0f; }
-			if (c > 1.2f) count_false++;
+			for (int k = 0; k < 8; ++k) {
+				const float c = CM(k, v);
+				if (c < thr) { tmpw += __expf((c * c) * -5.5555553436279296875f); count += 1.0f; }
+				if (c > 1.2f) count_false++;
+			}
+			float p = 0.0f;
+			if (count > 2.0f && count_false < 3) p = tmpw * rcpf(count);
+			else if (count_false < 3) p = thr_fallback;
+			p = p * prior;
+			PROB(v) = p;
+			prob_sum += p;
 		}
-		float p = 0.0f;
-		if (count > 2.0f && count_false < 3) p = tmpw * rcpf(count);
-		else if (count_false < 3) p = thr_fallback;
-		p = p * prior;
-		PROB(v) = p;
-		prob_sum += p;
-	}
-	Rng rng = rng_load(a.rng, center);
-	VW vw; vw.lo = 0ull; vw.hi = 0ull;
-	{
-		const float inv = rcpf(prob_sum);
-		float cum = 0.0f;
-		for (int v = 0; v < S; ++v) { cum = fmaf(inv, PROB(v), cum); PROB(v) = cum; }   // TransformPDFToCDF
-		for (int s = 0; s < 15; ++s) {
-			const float r = rng_uniform(rng) - 1.1920928955078125e-07f;
-			for (int v = 0; v < S; ++v) if (PROB(v) > r) { vw_add(vw, v); break; }
+		rng = rng_load(a.rng, center);
+		{
+			const float inv = rcpf(prob_sum);
+			float cum = 0.0f;
+			for (int v = 0; v < S; ++v) { cum = fmaf(inv, PROB(v), cum); PROB(v) = cum; }   // TransformPDFToCDF
+			for (int s = 0; s < 15; ++s) {
+				const float r = rng_uniform(rng) - 1.1920928955078125e-07f;
+				for (int v = 0; v < S; ++v) if (PROB(v) > r) { vw_add(vw, v); break; }
+			}
 		}
-	}
-	uint32_t temp_sel = 0u; float weight_norm = 0.0f;
-	for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) { temp_sel |= 1u << v; weight_norm += (float)w; } }
-	const float inv_wn = rcpf(weight_norm);
-
-	float best_cost; int best_k;
-	{
+		float weight_norm = 0.0f;
+		for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) { temp_sel |= 1u << v; weight_norm += (float)w; } }
+		inv_wn = rcpf(weight_norm);
 		float fc[8];
 #pragma unroll
 		for (int k = 0; k < 8; ++k) {
@@ -389,40 +395,45 @@ __global__ void __launch_bounds__(NT) k_strong(const Args a, const int iter, con
 	}
 
 	// ---- current hypothesis under the sampled views (views with weight 0 contribute exactly 0)
-	float4 pl_now = a.planes[center];
+	float4 pl_now = make_float4(0.f, 0.f, 1.f, 1.f);
+	if (alive) pl_now = a.planes[center];
 	float cost_now;
 	{
 		float acc = 0.0f;
+#pragma unroll 1
 		for (int v = 0; v < S; ++v) {
 			const int w = vw_get(vw, v);
-			if (w == 0) continue;
-			const Homog Hm = make_homography(rc, sv[v], pl_now);
-			acc = fmaf((float)w, ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, lx, ly, px, py, inv36), acc);
+			const float c = NCC(v, pl_now, alive && w > 0);
+			if (w > 0) acc = fmaf((float)w, c, acc);
 		}
 		cost_now = acc * inv_wn;
 	}
 	const float cost_stored = cost_now;                   // costs[center] = cost_now (APD.cu:1295)
-	float depth_now = plane_depth(rc, pl_now, xf, yf);
+	float depth_now = 1.0f;
 	uint32_t sel_out = 0u; bool sel_write = false;
-	if ((flags >> best_k) & 1u) {
-		int bp = pos[0];
+	float depth_rand = 1.0f, depth_pert = 1.0f;
+	float4 n_rand = pl_now, n_pert = pl_now;
+	if (alive) {
+		depth_now = plane_depth(rc, pl_now, xf, yf);
+		if ((flags >> best_k) & 1u) {
+			int bp = pos[0];
 #pragma unroll
-		for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
-		const float4 cand = a.planes[bp];
-		const float d = plane_depth(rc, cand, xf, yf);
-		if (d >= a.depth_min && d <= a.depth_max && best_cost < cost_now) {
-			depth_now = d; pl_now = cand; cost_now = best_cost; sel_out = temp_sel; sel_write = true;
+			for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
+			const float4 cand = a.planes[bp];
+			const float d = plane_depth(rc, cand, xf, yf);
+			if (d >= a.depth_min && d <= a.depth_max && best_cost < cost_now) {
+				depth_now = d; pl_now = cand; cost_now = best_cost; sel_out = temp_sel; sel_write = true;
+			}
 		}
-	}
-
-	// ---- PlaneHypothesisRefinementStrong, APD.cu:837-890
-	{
-		const float depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
-		const float4 n_rand = random_normal(rc, xf, yf, rng, depth_now);
+		// PlaneHypothesisRefinementStrong, APD.cu:837-890
+		depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
+		n_rand = random_normal(rc, xf, yf, rng, depth_now);
 		const float lo = depth_now * (1.0f - 0.02f);
 		const float span = fmaf(depth_now, 1.0f + 0.02f, -lo);
-		const float depth_pert = fmaf(span, rng_uniform(rng), lo);     // the do/while never repeats (:860-862)
-		const float4 n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
+		depth_pert = fmaf(span, rng_uniform(rng), lo);     // the do/while never repeats (:860-862)
+		n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
+	}
+	{
 		const float4 n0 = pl_now; const float d0 = depth_now;
 #pragma unroll 1
 		for (int i = 0; i < 5; ++i) {
@@ -430,17 +441,18 @@ __global__ void __launch_bounds__(NT) k_strong(const Args a, const int iter, con
 			float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
 			t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
 			float acc = 0.0f;
+#pragma unroll 1
 			for (int v = 0; v < S; ++v) {
 				const int w = vw_get(vw, v);
-				if (w == 0) continue;
-				const Homog Hm = make_homography(rc, sv[v], t);
-				acc = fmaf((float)w, ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, lx, ly, px, py, inv36), acc);
+				const float c = NCC(v, t, alive && w > 0);
+				if (w > 0) acc = fmaf((float)w, c, acc);
 			}
 			const float tc = acc * inv_wn;
 			const float d = plane_depth(rc, t, xf, yf);
 			if (d >= a.depth_min && d <= a.depth_max && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
 		}
 	}
+	if (!alive) return;
 	rng_store(a.rng, center, rng);
 	vw_store(a.view_w, center, vw);
 	if (sel_write) a.sel_views[center] = sel_out;
@@ -452,6 +464,7 @@ __global__ void __launch_bounds__(NT) k_strong(const Args a, const int iter, con
 	}
 #undef CM
 #undef PROB
+#undef NCC
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -711,8 +724,8 @@ cudaError_t launch_init_planes(cudaStream_t st, const Args &a) {
 }
 cudaError_t launch_strong(cudaStream_t st, const Args &a, int iter, int color) {
 	using C = TileCfg<kHalfTW, kHalfTH>;
-	constexpr int NT = 256;
-	const size_t smem = C::ELEMS * 4 + smem_common(a.S) + (size_t)9 * a.S * NT * 4;
+	constexpr int NT = 128;
+	const size_t smem = C::ELEMS * 4 + (NT / 32) * kPatchFloats * 4 + smem_common(a.S);
 	if (smem > 227 * 1024) return cudaErrorInvalidValue;
 	cudaFuncSetAttribute(k_strong<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 g((a.W + kHalfTW - 1) / kHalfTW, (a.H + kHalfTH - 1) / kHalfTH);
