@@ -358,4 +358,11 @@ __device__ __forceinline__ int vw_get(const VW &w, int v) { return (int)(((v < 1
 __device__ __forceinline__ VW vw_load(const uint4 *g, size_t i) { uint4 u = g[i]; VW w; w.lo = ((unsigned long long)u.y << 32) | u.x; w.hi = ((unsigned long long)u.w << 32) | u.z; return w; }
 __device__ __forceinline__ void vw_store(uint4 *g, size_t i, const VW &w) { g[i] = make_uint4((uint32_t)w.lo, (uint32_t)(w.lo >> 32), (uint32_t)w.hi, (uint32_t)(w.hi >> 32)); }
 
+// bitmask of the views with a non-zero sampling weight
+__device__ __forceinline__ uint32_t vw_mask(const VW &w, int S) {
+	uint32_t m = 0u;
+	for (int v = 0; v < S; ++v) if (vw_get(w, v) > 0) m |= 1u << v;
+	return m;
+}
+
 }  // namespace apd

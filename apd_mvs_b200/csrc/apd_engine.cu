@@ -21,6 +21,7 @@ void launch_depth_normal(cudaStream_t, const Args &);
 void launch_median(cudaStream_t, const Args &, int color);
 cudaError_t launch_classify(cudaStream_t, const Args &);
 cudaError_t launch_local_refine(cudaStream_t, const Args &);
+cudaError_t launch_sweep(cudaStream_t, const Args &, int mode);
 // deformation path (apd_kernels_weak.cu)
 cudaError_t launch_nearest_strong(cudaStream_t, const Args &);
 cudaError_t launch_gen_anchors(cudaStream_t, const Args &);
@@ -325,8 +326,10 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	launch_depth_normal(st, a); h->launches++; STAGE_END();                                                // K11
 	launch_median(st, a, 0); h->launches++; STAGE_END();                                                   // K12
 	launch_median(st, a, 1); h->launches++; STAGE_END();                                                   // K13
-	CKH(launch_classify(st, a)); h->launches++; STAGE_END();                                               // K14
-	CKH(launch_local_refine(st, a)); h->launches++; STAGE_END();                                           // K15
+	// K14 and K15 are one fused launch (reported in the K14 slot) unless the run stops between them
+	if (stage_end == stage) { CKH(launch_sweep(st, a, 0)); h->launches++; STAGE_END(); }                   // K14 alone
+	CKH(launch_sweep(st, a, 2)); h->launches++; STAGE_END();                                               // K14 + K15
+	STAGE_END();
 #undef STAGE_END
 done:
 	CKH(cudaStreamSynchronize(st));

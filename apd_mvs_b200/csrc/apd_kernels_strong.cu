@@ -19,6 +19,7 @@
 //     weight are skipped in the 6 post-selection evaluations (their weight multiplies them by 0);
 //   * no host synchronisation between launches.
 #include <curand_kernel.h>
+#include <cstdlib>
 #include "apd_device.cuh"
 
 namespace apd {
@@ -397,14 +398,21 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 	// ---- current hypothesis under the sampled views (views with weight 0 contribute exactly 0)
 	float4 pl_now = make_float4(0.f, 0.f, 1.f, 1.f);
 	if (alive) pl_now = a.planes[center];
+	// Each lane walks ITS OWN list of sampled views (ascending, as the reference's sum does); lanes of a warp
+	// are at different views at the same time, which the layered texture (per-lane layer) permits. The warp
+	// iterates max-over-lanes(#sampled views) times instead of S times.
+	const uint32_t wmask = alive ? temp_sel : 0u;
 	float cost_now;
 	{
 		float acc = 0.0f;
+		uint32_t m = wmask;
 #pragma unroll 1
-		for (int v = 0; v < S; ++v) {
-			const int w = vw_get(vw, v);
-			const float c = NCC(v, pl_now, alive && w > 0);
-			if (w > 0) acc = fmaf((float)w, c, acc);
+		while (__any_sync(0xffffffffu, m != 0u)) {
+			const bool want = m != 0u;
+			const int v = want ? (__ffs(m) - 1) : 0;
+			m &= m - 1u;
+			const float c = NCC(v, pl_now, want);
+			if (want) acc = fmaf((float)vw_get(vw, v), c, acc);
 		}
 		cost_now = acc * inv_wn;
 	}
@@ -441,11 +449,14 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 			float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
 			t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
 			float acc = 0.0f;
+			uint32_t m = wmask;
 #pragma unroll 1
-			for (int v = 0; v < S; ++v) {
-				const int w = vw_get(vw, v);
-				const float c = NCC(v, t, alive && w > 0);
-				if (w > 0) acc = fmaf((float)w, c, acc);
+			while (__any_sync(0xffffffffu, m != 0u)) {
+				const bool want = m != 0u;
+				const int v = want ? (__ffs(m) - 1) : 0;
+				m &= m - 1u;
+				const float c = NCC(v, t, want);
+				if (want) acc = fmaf((float)vw_get(vw, v), c, acc);
 			}
 			const float tc = acc * inv_wn;
 			const float d = plane_depth(rc, t, xf, yf);
@@ -695,6 +706,143 @@ __global__ void __launch_bounds__(kFullNT) k_local_refine(const Args a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K14 + K15 fused (used by full runs). LocalRefine's 11 disparity steps are the centre of DepthToWeak's
+// 61-step sweep: same planes, same NCC values (and the same geometric term), only the weighted
+// accumulation differs when geom_consistency is on (APD.cu:2074-2078 vs :2217-2220). Each NCC is
+// therefore evaluated once and fed to both accumulators. The two kernels touch disjoint state (K14
+// writes pixel states, K15 the depth of its own pixel; neither reads what the other writes), so the
+// fusion is exact. All threads stay in the loops: fetches are quad-cooperative (ncc6_quad).
+constexpr int kSweepTW = 16, kSweepTH = 8, kSweepNT = 128;
+
+template <bool DO14, bool DO15, bool COOP>
+__global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a) {
+	using C = TileCfg<kSweepTW, kSweepTH>;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float *tile = reinterpret_cast<float *>(smem_raw);
+	float *patch = tile + C::ELEMS;
+	RefConst *sr = reinterpret_cast<RefConst *>(patch + (kSweepNT / 32) * kPatchFloats);
+	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
+	float *prof = reinterpret_cast<float *>(sv + a.S);        // [61][NT] cost profile (K14)
+	const int tid = threadIdx.y * kSweepTW + threadIdx.x;
+	const int x0 = blockIdx.x * kSweepTW, y0 = blockIdx.y * kSweepTH;
+	load_tile<kSweepTW, kSweepTH, kSweepNT>(a, tile, x0, y0, tid);
+	load_views(a, sv, sr, tid, kSweepNT);
+	__syncthreads();
+	const QuadCtx qc = make_quad_ctx(patch, tid);
+	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
+	const int lx = threadIdx.x, ly = threadIdx.y;
+	const bool in_img = px < a.W && py < a.H;
+	const size_t center = (size_t)py * a.W + px;
+	const RefConst &rc = *sr;
+	const float xf = (float)px, yf = (float)py;
+	const float inv36 = a.inv_w[0];
+	const int S = a.S;
+	uint32_t bits = 0u; VW vw; vw.lo = 0ull; vw.hi = 0ull;
+	SweepCtx c; c.pl = make_float4(0.f, 0.f, 1.f, 1.f); c.depth = 1.0f; c.weight_normal = 0.0f; c.kb = 1.0f; c.disp = 1.0f; c.valid = 0;
+	bool has_depth = false;
+	if (in_img) {
+		bits = a.sel_views[center];
+		vw = vw_load(a.view_w, center);
+		has_depth = sweep_setup(a, rc, sv, center, bits, vw, c);
+	}
+	const bool border = px < 6 || py < 6 || px >= a.W - 6 || py >= a.H - 6;
+	const bool on14 = DO14 && in_img && !border && has_depth && c.valid > 0;
+	const bool on15 = DO15 && in_img && has_depth && c.valid > 0 && c.weight_normal != 0.0f;
+	const float inv_wn = rcpf(c.weight_normal);
+	const uint32_t act = bits & vw_mask(vw, S);
+	float *p = prof + tid;
+	float min_cost15 = 2.0f, best_depth = c.depth;
+#pragma unroll 1
+	for (int k = -30; k <= 30; ++k) {
+		const float d = c.kb * rcpf(c.disp + (float)k);
+		const bool in_range = !(d < a.depth_min || d > a.depth_max);
+		const bool near = (k >= -5 && k <= 5);
+		// profile entries 0 and 60 (k = -30, +30) are never read by the peak analysis (APD.cu:2101-2110 touches 1..59)
+		const bool need = in_range && ((on14 && k > -30 && k < 30) || (on15 && near));
+		float4 t = c.pl;
+		t.w = plane_offset(rc, xf, yf, d, t.x, t.y, t.z);
+		float acc14 = 0.0f, acc15 = 0.0f;
+		// per-lane list of the views that count: selected AND sampled (a zero weight multiplies the cost by 0 in
+		// the reference); ascending order = the reference's summation order
+		uint32_t m = need ? act : 0u;
+#pragma unroll 1
+		while (__any_sync(0xffffffffu, m != 0u)) {
+			const bool want = m != 0u;
+			const int v = want ? (__ffs(m) - 1) : 0;
+			m &= m - 1u;
+			const int w = vw_get(vw, v);
+			float ncc = kCostMax;
+			if (COOP) ncc = ncc6_quad(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
+			else if (want) ncc = ncc_strong<5, 2>(a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], tile, C::PW, lx, ly, px, py, inv36);
+			if (want) {
+				float g = 0.0f;
+				if (a.geom) g = geom_cost(a, rc, sv[v], v + 1, t, xf, yf);
+				if (DO14) acc14 = fmaf((float)w, a.geom ? fmaf(a.geom_factor, g, ncc) : ncc, acc14);          // APD.cu:2074-2078
+				if (DO15) { acc15 = fmaf((float)w, ncc, acc15); if (a.geom) acc15 = fmaf((float)w, a.geom_factor * g, acc15); }   // :2217-2220
+			}
+		}
+		if (DO14 && on14) {
+			float pc = 2.0f;
+			if (in_range) { pc = acc14 * inv_wn; pc = (2.0f > pc) ? pc : 2.0f; }      // OpenCV MIN(2.0f, p_cost)
+			p[(k + 30) * kSweepNT] = pc;
+		}
+		if (DO15 && on15 && near && in_range) {
+			const float tc = acc15 * inv_wn;
+			if (tc < min_cost15) { min_cost15 = tc; best_depth = d; }
+		}
+	}
+	if (DO15) {
+		// cost of the current depth (APD.cu:2173-2182): the compiler hoisted normal.z * depth out of the view
+		// loop there as a rounded product, so the plane offset is -((d*nz) + fma(X0,nx,X1*ny))
+		float4 t = c.pl;
+		{ float X0, X1; backproject(rc, xf, yf, c.depth, X0, X1); t.w = -((c.depth * t.z) + fmaf(X0, t.x, X1 * t.y)); }
+		float cost_sum = 0.0f;
+		uint32_t m = on15 ? act : 0u;
+#pragma unroll 1
+		while (__any_sync(0xffffffffu, m != 0u)) {
+			const bool want = m != 0u;
+			const int v = want ? (__ffs(m) - 1) : 0;
+			m &= m - 1u;
+			const int w = vw_get(vw, v);
+			float tc = kCostMax;
+			if (COOP) tc = ncc6_quad(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
+			else if (want) tc = ncc_strong<5, 2>(a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], tile, C::PW, lx, ly, px, py, inv36);
+			if (want) {
+				if (a.geom) tc = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, t, xf, yf), tc);
+				cost_sum = fmaf((float)w, tc, cost_sum);
+			}
+		}
+		if (on15) {
+			const float diff = fmaf(inv_wn, cost_sum, -min_cost15);   // (cost_now / weight_normal) - min_cost, one FFMA
+			if ((double)diff > 0.1) a.planes[center].w = best_depth;
+		}
+	}
+	if (DO14 && in_img) {
+		uint8_t out = APD_UNKNOWN;
+		if (on14) {   // peak analysis, APD.cu:2092-2143
+			int peak_count = 0, min_peak = 0; float min_cost = 2.0f;
+			unsigned long long peaks = 0ull;
+			for (int i = 2; i < 59; ++i) {
+				const float ci = p[i * kSweepNT];
+				if (p[(i - 1) * kSweepNT] > ci && p[(i + 1) * kSweepNT] > ci) {
+					peaks |= 1ull << i; peak_count++;
+					if (ci < min_cost) { min_peak = i; min_cost = ci; }
+				}
+			}
+			if (abs(min_peak - 30) > a.weak_peak_radius || p[min_peak * kSweepNT] > 0.5f) out = APD_WEAK;
+			else if (peak_count == 1) out = (p[min_peak * kSweepNT] <= 0.15f) ? APD_STRONG : APD_WEAK;
+			else {
+				float var = 0.0f;
+				for (int i = 2; i < 59; ++i) if (((peaks >> i) & 1ull) && i != min_peak) { const float dd = p[i * kSweepNT] - min_cost; var = fmaf(dd, dd, var); }
+				var = sqrtaf(var) * rcpf((float)(peak_count - 1));
+				out = (var > 0.2f) ? APD_STRONG : APD_WEAK;
+			}
+		}
+		a.states[center] = out;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 static inline size_t smem_common(int S) { return sizeof(RefConst) + (size_t)S * sizeof(ViewConst); }
 
@@ -746,6 +894,18 @@ cudaError_t launch_classify(cudaStream_t st, const Args &a) {
 	cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
 	k_classify<<<g, b, smem, st>>>(a);
+	return cudaGetLastError();
+}
+// mode 0: K14 only, 1: K15 only, 2: K14+K15 fused
+cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode) {
+	using C = TileCfg<kSweepTW, kSweepTH>;
+	const size_t smem = C::ELEMS * 4 + (kSweepNT / 32) * kPatchFloats * 4 + smem_common(a.S) + (size_t)61 * kSweepNT * 4;
+	dim3 b(kSweepTW, kSweepTH), g((a.W + kSweepTW - 1) / kSweepTW, (a.H + kSweepTH - 1) / kSweepTH);
+	static const bool coop = getenv("APD_SWEEP_SIMPLE") == nullptr;   // cooperative fetch is the default (A/B measured: 16.9 vs 22.4 ms)
+#define SWEEP_LAUNCH(A, B, Cc) do { cudaFuncSetAttribute(k_sweep<A, B, Cc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_sweep<A, B, Cc><<<g, b, smem, st>>>(a); } while (0)
+	if (coop) { if (mode == 0) SWEEP_LAUNCH(true, false, true); else if (mode == 1) SWEEP_LAUNCH(false, true, true); else SWEEP_LAUNCH(true, true, true); }
+	else { if (mode == 0) SWEEP_LAUNCH(true, false, false); else if (mode == 1) SWEEP_LAUNCH(false, true, false); else SWEEP_LAUNCH(true, true, false); }
+#undef SWEEP_LAUNCH
 	return cudaGetLastError();
 }
 cudaError_t launch_local_refine(cudaStream_t st, const Args &a) {
