@@ -28,7 +28,9 @@ struct ViewConst {
 	float wf, hf;       // float(width), float(height) of the source image (APD.cu:546)
 	float baseline;     // |c_ref - c_src| as DepthToWeak/LocalRefine compute it (APD.cu:2037-2042)
 	apd_camera cam;     // full source camera for the geometric-consistency term (APD.cu:752-789)
+	float pad_;         // 49-float stride: lanes reading the same field of different views hit different banks
 };
+static_assert(sizeof(ViewConst) == 49 * 4, "ViewConst stride");
 
 struct RefConst {
 	apd_camera cam;
@@ -265,64 +267,75 @@ __device__ __forceinline__ QuadCtx make_quad_ctx(float *patch_base, int tid) {
 	return q;
 }
 
+template <int SPT = 4, bool ROLL = true>
 __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc, bool want,
                                            const float *tile, int pitch, int lx, int ly, int px, int py, float inv_w) {
 	// must be called by all 32 lanes of the warp convergently
 	const bool active = want && centre_inside(Hm, vc, (float)px, (float)py);
 	const unsigned ballot = __ballot_sync(0xffffffffu, active);
 	const unsigned my_quad = (ballot >> (q.lane & ~3)) & 0xFu;      // which of my quad's four evaluation slots are live
-	float v[4][9];
-	// phase 1: all 36 fetches of the four evaluations are issued before any result is consumed
+	// SPT evaluation slots per trip: 9*SPT fetches are in flight before any result is consumed.
+#pragma unroll 1
+	for (int e0 = 0; e0 < 4; e0 += SPT) {
+		float v[SPT][9];
 #pragma unroll
-	for (int e = 0; e < 4; ++e) {
-		if ((ballot & (0x11111111u << e)) == 0u) continue;            // warp-uniform: nobody owns a live slot e
-		float h[9];
+		for (int u = 0; u < SPT; ++u) {
+			const int e = e0 + u;
+			if ((ballot & (0x11111111u << e)) == 0u) continue;            // warp-uniform: nobody owns a live slot e
+			float h[9];
 #pragma unroll
-		for (int i = 0; i < 9; ++i) h[i] = __shfl_sync(0xffffffffu, Hm.h[i], e, 4);
-		const int pxe = __shfl_sync(0xffffffffu, px, e, 4), pye = __shfl_sync(0xffffffffu, py, e, 4), lay = __shfl_sync(0xffffffffu, layer, e, 4);
-		if ((my_quad >> e) & 1u) {
-			const int qd = q.ql ^ e;
-			const int x0 = pxe - 5 + 2 * (qd & 1), y0 = pye - 5 + 2 * (qd >> 1);
+			for (int i = 0; i < 9; ++i) h[i] = __shfl_sync(0xffffffffu, Hm.h[i], e, 4);
+			const int pxe = __shfl_sync(0xffffffffu, px, e, 4), pye = __shfl_sync(0xffffffffu, py, e, 4), lay = __shfl_sync(0xffffffffu, layer, e, 4);
+			if ((my_quad >> e) & 1u) {
+				const int qd = q.ql ^ e;
+				const int x0 = pxe - 5 + 2 * (qd & 1), y0 = pye - 5 + 2 * (qd >> 1);
 #pragma unroll
-			for (int c = 0; c < 3; ++c) {
-				const float xf = (float)(x0 + 4 * c);
-				const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
+				for (int c = 0; c < 3; ++c) {
+					const float xf = (float)(x0 + 4 * c);
+					const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
 #pragma unroll
-				for (int d = 0; d < 3; ++d) v[e][c * 3 + d] = src_tap(tex, lay, h, ax, ay, az, (float)(y0 + 4 * d));
+					for (int d = 0; d < 3; ++d) v[u][c * 3 + d] = src_tap(tex, lay, h, ax, ay, az, (float)(y0 + 4 * d));
+				}
 			}
 		}
-	}
-	// phase 2: stage the warped patches: tap (2c+qa, 2d+qb) -> T = 12c + 2d + 6qa + qb, slot T*32 + lane
+		// stage the warped patches: tap (2c+qa, 2d+qb) -> T = 12c + 2d + 6qa + qb, slot T*32 + lane
 #pragma unroll
-	for (int e = 0; e < 4; ++e) {
-		if ((my_quad >> e) & 1u) {
-			const int qd = q.ql ^ e;
-			float *dst = q.slab + (6 * (qd & 1) + (qd >> 1)) * 32 + q.lane;
+		for (int u = 0; u < SPT; ++u) {
+			const int e = e0 + u;
+			if ((my_quad >> e) & 1u) {
+				const int qd = q.ql ^ e;
+				float *dst = q.slab + (6 * (qd & 1) + (qd >> 1)) * 32 + q.lane;
 #pragma unroll
-			for (int c = 0; c < 3; ++c)
+				for (int c = 0; c < 3; ++c)
 #pragma unroll
-				for (int d = 0; d < 3; ++d) dst[(12 * c + 2 * d) * 32] = v[e][c * 3 + d];
+					for (int d = 0; d < 3; ++d) dst[(12 * c + 2 * d) * 32] = v[u][c * 3 + d];
+			}
 		}
 	}
 	__syncwarp();
 	float cost = kCostMax;
 	if (active) {
 		NccSums t = {0.f, 0.f, 0.f, 0.f, 0.f};
-		const float *base = tile + (ly + kHalo) * pitch + (lx + kHalo);
+		const float *base = tile + (ly + kHalo) * pitch + (lx + kHalo) - 5 * pitch - 5;
 		const float *s0 = q.slab + q.lane, *s1 = q.slab + (q.lane ^ 1), *s2 = q.slab + (q.lane ^ 2), *s3 = q.slab + (q.lane ^ 3);
+		// ROLL keeps the accumulation loop small for the instruction cache (two x-offsets per trip)
+#pragma unroll(ROLL ? 1 : 3)
+		for (int i2 = 0; i2 < 3; ++i2) {
 #pragma unroll
-		for (int i = 0; i < 6; ++i) {
-			NccSums r = {0.f, 0.f, 0.f, 0.f, 0.f};
+			for (int ii = 0; ii < 2; ++ii) {
+				NccSums r = {0.f, 0.f, 0.f, 0.f, 0.f};
+				const float *rb = base + 2 * (2 * i2 + ii);
+				const float *sa = (ii == 0 ? s0 : s1) + (2 * i2 + ii) * 6 * 32;      // quadrant = (i&1) + 2*(j&1)
+				const float *sb = (ii == 0 ? s2 : s3) + (2 * i2 + ii) * 6 * 32;
 #pragma unroll
-			for (int j = 0; j < 6; ++j) {
-				const float rp = base[(2 * j - 5) * pitch + (2 * i - 5)];
-				const int quad = (i & 1) + 2 * (j & 1);
-				const float *sq = quad == 0 ? s0 : quad == 1 ? s1 : quad == 2 ? s2 : s3;
-				const float sp = sq[(i * 6 + j) * 32];
-				r.r += rp; r.rr = fmaf(rp, rp, r.rr); r.rs = fmaf(rp, sp, r.rs);
-				r.s += sp; r.ss = fmaf(sp, sp, r.ss);
+				for (int j = 0; j < 6; ++j) {
+					const float rp = rb[2 * j * pitch];
+					const float sp = ((j & 1) ? sb : sa)[j * 32];
+					r.r += rp; r.rr = fmaf(rp, rp, r.rr); r.rs = fmaf(rp, sp, r.rs);
+					r.s += sp; r.ss = fmaf(sp, sp, r.ss);
+				}
+				t.r += r.r; t.rr += r.rr; t.s += r.s; t.ss += r.ss; t.rs += r.rs;
 			}
-			t.r += r.r; t.rr += r.rr; t.s += r.s; t.ss += r.ss; t.rs += r.rs;
 		}
 		cost = ncc_cost(t, inv_w);
 	}

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 	float *cmt = cm + tid;
 #define CM(k, v) cmt[((k) * S + (v)) * NT]
 #define PROB(v) cmt[(8 * S + (v)) * NT]
-#define NCC(v, plane, want) ncc6_quad(qc, a.img_tex, (v) + 1, make_homography(rc, sv[v], plane), sv[v], want, tile, C::PW, lx, ly, px, py, inv36)
+#define NCC(v, plane, want) ncc6_quad<4, true>(qc, a.img_tex, (v) + 1, make_homography(rc, sv[v], plane), sv[v], want, tile, C::PW, lx, ly, px, py, inv36)
 
 	// ---- adaptive checkerboard sampling: 8 candidates (0 up_near 1 up_far 2 down_near 3 down_far
 	//      4 left_near 5 left_far 6 right_near 7 right_far)
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a) {
 			m &= m - 1u;
 			const int w = vw_get(vw, v);
 			float ncc = kCostMax;
-			if (COOP) ncc = ncc6_quad(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
+			if (COOP) ncc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
 			else if (want) ncc = ncc_strong<5, 2>(a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], tile, C::PW, lx, ly, px, py, inv36);
 			if (want) {
 				float g = 0.0f;
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a) {
 			m &= m - 1u;
 			const int w = vw_get(vw, v);
 			float tc = kCostMax;
-			if (COOP) tc = ncc6_quad(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
+			if (COOP) tc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
 			else if (want) tc = ncc_strong<5, 2>(a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], tile, C::PW, lx, ly, px, py, inv36);
 			if (want) {
 				if (a.geom) tc = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, t, xf, yf), tc);
