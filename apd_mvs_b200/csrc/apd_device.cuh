@@ -16,7 +16,8 @@
 
 namespace apd {
 
-constexpr int kRefPad = 8;        // replicated border of the pitch-linear reference-image copy
+constexpr int kRefPad = 9;        // replicated border of the pitch-linear reference-image copy; 9 - kHalo = 4 keeps every
+                                  // TMA box origin (x0 - 5 + 9, x0 a multiple of 16) 16-byte aligned, which the hardware demands
 constexpr int kHalo = 5;          // strong_radius (main.h:83)
 constexpr float kCostMax = 2.0f;
 

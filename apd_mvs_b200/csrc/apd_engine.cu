@@ -5,6 +5,7 @@
 // re-allocates ~25 buffers + 2N cudaArrays per (view, pass)). No host synchronisation between
 // the launches of a run; stage timing is taken with events on the handle's stream.
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include <string>
 #include <vector>
 #include <cstring>
@@ -16,12 +17,13 @@ void launch_setup_views(cudaStream_t, const apd_camera *, int, ViewConst *, RefC
 void launch_pad_ref(cudaStream_t, const float *, int, int, int, float *, int, int);
 void launch_rng_seed(cudaStream_t, const Args &, unsigned long long);
 cudaError_t launch_init_planes(cudaStream_t, const Args &);
-cudaError_t launch_strong(cudaStream_t, const Args &, int iter, int color);
+cudaError_t launch_strong(cudaStream_t, const Args &, int iter, int color, const CUtensorMap *);
+int make_tensor_maps(const float *, int, int, CUtensorMap *, CUtensorMap *);
 void launch_depth_normal(cudaStream_t, const Args &);
 void launch_median(cudaStream_t, const Args &, int color);
 cudaError_t launch_classify(cudaStream_t, const Args &);
 cudaError_t launch_local_refine(cudaStream_t, const Args &);
-cudaError_t launch_sweep(cudaStream_t, const Args &, int mode);
+cudaError_t launch_sweep(cudaStream_t, const Args &, int mode, const CUtensorMap *);
 // deformation path (apd_kernels_weak.cu)
 cudaError_t launch_nearest_strong(cudaStream_t, const Args &);
 cudaError_t launch_gen_anchors(cudaStream_t, const Args &);
@@ -50,6 +52,7 @@ struct apd_engine {
 	uint2 *rng = nullptr; uint4 *view_w = nullptr;
 	short2 *anchors = nullptr, *nearest = nullptr;
 	float *scratch = nullptr;
+	CUtensorMap tmap_strong, tmap_sweep;
 	bool have_images = false, have_cams = false, have_depths = false, have_planes = false, have_states = false;
 	std::vector<cudaEvent_t> events;
 	std::vector<float> stage_ms;
@@ -133,6 +136,7 @@ extern "C" int apd_create(apd_handle *out, int device, int width, int height, in
 	}
 #undef ALLOC
 	if (make_layered(h, &h->img_arr, &h->img_tex) != APD_OK) return bail(APD_E_CUDA);
+	if (make_tensor_maps(h->ref_pad, h->ref_pitch, h->ref_rows, &h->tmap_strong, &h->tmap_sweep) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return bail(APD_E_CUDA); }
 	cudaMemsetAsync(h->costs, 0, n * 4, h->stream);
 	cudaMemsetAsync(h->view_w, 0, n * 16, h->stream);
 	cudaMemsetAsync(h->planes, 0, n * 16, h->stream);
@@ -317,8 +321,8 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	if (apd_on) { CKH(launch_demote_unreliable(st, a)); h->launches++; } STAGE_END();                      // 3  K4
 	CKH(launch_init_planes(st, a)); h->launches++; STAGE_END();                                            // 4  K5
 	for (int it = 0; it < p.max_iterations; ++it) {
-		CKH(launch_strong(st, a, it, 0)); h->launches++; STAGE_END();                                      // K6
-		CKH(launch_strong(st, a, it, 1)); h->launches++; STAGE_END();                                      // K7
+		CKH(launch_strong(st, a, it, 0, &h->tmap_strong)); h->launches++; STAGE_END();                                      // K6
+		CKH(launch_strong(st, a, it, 1, &h->tmap_strong)); h->launches++; STAGE_END();                                      // K7
 		if (apd_on) { CKH(launch_fit_plane(st, a)); h->launches++; } STAGE_END();                          // K8
 		if (apd_on) { CKH(launch_weak(st, a, it, 0)); h->launches++; } STAGE_END();                        // K9
 		if (apd_on) { CKH(launch_weak(st, a, it, 1)); h->launches++; } STAGE_END();                        // K10
@@ -327,8 +331,8 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	launch_median(st, a, 0); h->launches++; STAGE_END();                                                   // K12
 	launch_median(st, a, 1); h->launches++; STAGE_END();                                                   // K13
 	// K14 and K15 are one fused launch (reported in the K14 slot) unless the run stops between them
-	if (stage_end == stage) { CKH(launch_sweep(st, a, 0)); h->launches++; STAGE_END(); }                   // K14 alone
-	CKH(launch_sweep(st, a, 2)); h->launches++; STAGE_END();                                               // K14 + K15
+	if (stage_end == stage) { CKH(launch_sweep(st, a, 0, &h->tmap_sweep)); h->launches++; STAGE_END(); }                   // K14 alone
+	CKH(launch_sweep(st, a, 2, &h->tmap_sweep)); h->launches++; STAGE_END();                                               // K14 + K15
 	STAGE_END();
 #undef STAGE_END
 done:

@@ -19,6 +19,7 @@
 //     weight are skipped in the 6 post-selection evaluations (their weight multiplies them by 0);
 //   * no host synchronisation between launches.
 #include <curand_kernel.h>
+#include <cuda.h>
 #include <cstdlib>
 #include "apd_device.cuh"
 
@@ -129,6 +130,31 @@ __device__ __forceinline__ void load_views(const Args &a, ViewConst *sv, RefCons
 	const uint32_t *gr = reinterpret_cast<const uint32_t *>(a.ref);
 	uint32_t *srr = reinterpret_cast<uint32_t *>(sr);
 	for (int i = tid; i < (int)(sizeof(RefConst) / 4); i += nt) srr[i] = gr[i];
+}
+
+// ---- TMA staging of the reference tile ------------------------------------------------------------
+// The tile (+5 px halo) is one box of a 2-D tensor map over `ref_pad` (the reference image with a
+// replicated 8-px border, so clamp-to-edge needs no per-element bounds test); the part of a box that
+// overhangs the padded image is zero-filled by the hardware and never read. One elected thread arms an
+// mbarrier with the byte count and issues cp.async.bulk.tensor; every thread then waits on the barrier.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_barrier_init(uint64_t *mbar, int tid) {
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+}
+__device__ __forceinline__ void tma_load_tile(const CUtensorMap *tmap, float *tile, uint64_t *mbar, int cx, int cy, uint32_t bytes, int tid, uint32_t parity) {
+	if (tid == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+		             ::"r"(smem_u32(tile)), "l"(tmap), "r"(cx), "r"(cy), "r"(smem_u32(mbar)) : "memory");
+	}
+	uint32_t done = 0;
+	while (!done) {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,20 +271,22 @@ __device__ __forceinline__ void arm_try(ArmMin &m, const float *costs, int pos) 
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, const int color) {
+__global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, const int color, const __grid_constant__ CUtensorMap tmap) {
 	using C = TileCfg<kHalfTW, kHalfTH>;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	extern __shared__ __align__(128) unsigned char smem_raw[];      // no static smem in this kernel: the TMA destination must be 128-B aligned
 	float *tile = reinterpret_cast<float *>(smem_raw);
-	float *xchg = tile + C::ELEMS;                              // [NT/32][36][32] warped source patches
+	uint64_t &tile_bar = *reinterpret_cast<uint64_t *>(tile + C::ELEMS);
+	float *xchg = tile + C::ELEMS + 4;                              // [NT/32][36][32] warped source patches
 	RefConst *sr = reinterpret_cast<RefConst *>(xchg + (NT / 32) * kPatchFloats);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
 	const int tid = threadIdx.x;
 	// [9*S][NT] per block: 8xS cost matrix + S probabilities, in a global scratch slab that stays in L1/L2
 	float *cm = a.scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (9 * a.S * NT);
 	const int x0 = blockIdx.x * kHalfTW, y0 = blockIdx.y * kHalfTH;
-	load_tile<kHalfTW, kHalfTH, NT>(a, tile, x0, y0, tid);
+	tma_barrier_init(&tile_bar, tid);
 	load_views(a, sv, sr, tid, NT);
 	__syncthreads();
+	tma_load_tile(&tmap, tile, &tile_bar, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, C::ELEMS * 4, tid, 0);
 	const QuadCtx qc = make_quad_ctx(xchg, tid);
 	int px, py, lx, ly;
 	half_pixel(tid, x0, y0, color, px, py, lx, ly);
@@ -715,19 +743,21 @@ __global__ void __launch_bounds__(kFullNT) k_local_refine(const Args a) {
 constexpr int kSweepTW = 16, kSweepTH = 8, kSweepNT = 128;
 
 template <bool DO14, bool DO15, bool COOP>
-__global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a) {
+__global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __grid_constant__ CUtensorMap tmap) {
 	using C = TileCfg<kSweepTW, kSweepTH>;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	extern __shared__ __align__(128) unsigned char smem_raw[];      // no static smem in this kernel: the TMA destination must be 128-B aligned
 	float *tile = reinterpret_cast<float *>(smem_raw);
-	float *patch = tile + C::ELEMS;
+	uint64_t &tile_bar = *reinterpret_cast<uint64_t *>(tile + C::ELEMS);
+	float *patch = tile + C::ELEMS + 4;
 	RefConst *sr = reinterpret_cast<RefConst *>(patch + (kSweepNT / 32) * kPatchFloats);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
 	float *prof = reinterpret_cast<float *>(sv + a.S);        // [61][NT] cost profile (K14)
 	const int tid = threadIdx.y * kSweepTW + threadIdx.x;
 	const int x0 = blockIdx.x * kSweepTW, y0 = blockIdx.y * kSweepTH;
-	load_tile<kSweepTW, kSweepTH, kSweepNT>(a, tile, x0, y0, tid);
+	tma_barrier_init(&tile_bar, tid);
 	load_views(a, sv, sr, tid, kSweepNT);
 	__syncthreads();
+	tma_load_tile(&tmap, tile, &tile_bar, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, C::ELEMS * 4, tid, 0);
 	const QuadCtx qc = make_quad_ctx(patch, tid);
 	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
 	const int lx = threadIdx.x, ly = threadIdx.y;
@@ -870,14 +900,14 @@ cudaError_t launch_init_planes(cudaStream_t st, const Args &a) {
 	}
 	return cudaGetLastError();
 }
-cudaError_t launch_strong(cudaStream_t st, const Args &a, int iter, int color) {
+cudaError_t launch_strong(cudaStream_t st, const Args &a, int iter, int color, const CUtensorMap *tmap) {
 	using C = TileCfg<kHalfTW, kHalfTH>;
 	constexpr int NT = 128;
-	const size_t smem = C::ELEMS * 4 + (NT / 32) * kPatchFloats * 4 + smem_common(a.S);
+	const size_t smem = C::ELEMS * 4 + 16 + (NT / 32) * kPatchFloats * 4 + smem_common(a.S);
 	if (smem > 227 * 1024) return cudaErrorInvalidValue;
 	cudaFuncSetAttribute(k_strong<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 g((a.W + kHalfTW - 1) / kHalfTW, (a.H + kHalfTH - 1) / kHalfTH);
-	k_strong<NT><<<g, NT, smem, st>>>(a, iter, color);
+	k_strong<NT><<<g, NT, smem, st>>>(a, iter, color, *tmap);
 	return cudaGetLastError();
 }
 void launch_depth_normal(cudaStream_t st, const Args &a) {
@@ -897,12 +927,12 @@ cudaError_t launch_classify(cudaStream_t st, const Args &a) {
 	return cudaGetLastError();
 }
 // mode 0: K14 only, 1: K15 only, 2: K14+K15 fused
-cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode) {
+cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode, const CUtensorMap *tmap) {
 	using C = TileCfg<kSweepTW, kSweepTH>;
-	const size_t smem = C::ELEMS * 4 + (kSweepNT / 32) * kPatchFloats * 4 + smem_common(a.S) + (size_t)61 * kSweepNT * 4;
+	const size_t smem = C::ELEMS * 4 + 16 + (kSweepNT / 32) * kPatchFloats * 4 + smem_common(a.S) + (size_t)61 * kSweepNT * 4;
 	dim3 b(kSweepTW, kSweepTH), g((a.W + kSweepTW - 1) / kSweepTW, (a.H + kSweepTH - 1) / kSweepTH);
 	static const bool coop = getenv("APD_SWEEP_SIMPLE") == nullptr;   // cooperative fetch is the default (A/B measured: 16.9 vs 22.4 ms)
-#define SWEEP_LAUNCH(A, B, Cc) do { cudaFuncSetAttribute(k_sweep<A, B, Cc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_sweep<A, B, Cc><<<g, b, smem, st>>>(a); } while (0)
+#define SWEEP_LAUNCH(A, B, Cc) do { cudaFuncSetAttribute(k_sweep<A, B, Cc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_sweep<A, B, Cc><<<g, b, smem, st>>>(a, *tmap); } while (0)
 	if (coop) { if (mode == 0) SWEEP_LAUNCH(true, false, true); else if (mode == 1) SWEEP_LAUNCH(false, true, true); else SWEEP_LAUNCH(true, true, true); }
 	else { if (mode == 0) SWEEP_LAUNCH(true, false, false); else if (mode == 1) SWEEP_LAUNCH(false, true, false); else SWEEP_LAUNCH(true, true, false); }
 #undef SWEEP_LAUNCH
@@ -915,6 +945,28 @@ cudaError_t launch_local_refine(cudaStream_t st, const Args &a) {
 	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
 	k_local_refine<<<g, b, smem, st>>>(a);
 	return cudaGetLastError();
+}
+
+
+// Tensor maps over the padded reference image, one per tile shape (box = tile + halo, row pitch of the box = TileCfg::PW).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_map(PFN_encodeTiled enc, CUtensorMap *m, const float *base, int pitch_elems, int rows, int box_w, int box_h) {
+	cuuint64_t dims[2] = {(cuuint64_t)pitch_elems, (cuuint64_t)rows};
+	cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 4};
+	cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+	cuuint32_t estr[2] = {1, 1};
+	return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
+}
+int make_tensor_maps(const float *ref_pad, int pitch_elems, int rows, CUtensorMap *strong, CUtensorMap *sweep) {
+	void *fn = nullptr; cudaDriverEntryPointQueryResult qres;
+	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+	PFN_encodeTiled enc = (PFN_encodeTiled)fn;
+	using CS = TileCfg<kHalfTW, kHalfTH>; using CW = TileCfg<kSweepTW, kSweepTH>;
+	if (encode_map(enc, strong, ref_pad, pitch_elems, rows, CS::PW, CS::PH)) return -1;
+	if (encode_map(enc, sweep, ref_pad, pitch_elems, rows, CW::PW, CW::PH)) return -1;
+	return 0;
 }
 
 }  // namespace apd
