@@ -101,9 +101,10 @@ __global__ void k_rng_seed(uint2 *rng, int W, int H, unsigned long long seed) {
 // Shared-memory staging of the reference tile (+5 px halo) and of the per-view constants.
 template <int TW, int TH>
 struct TileCfg {
-	// row pitch: multiple of 16 B and = 8 (mod 16) floats, which makes the reference-window reads of a
-	// warp (16x4 pixels, one colour, rows of alternating parity) bank-conflict free
-	static constexpr int PW = ((TW + 2 * kHalo + 7) / 16) * 16 + 8;
+	// Row pitch (floats), multiple of 16 B, chosen so that the reference-window reads of a warp are bank-conflict
+	// free: the checkerboard kernels (TW = 32: a warp = 16x4 pixels of one colour, rows of alternating parity) need
+	// pitch = 8 (mod 16); the full-grid kernels (TW = 16: a warp = two rows of 16 pixels) need pitch = 16 (mod 32).
+	static constexpr int PW = (TW == 16) ? 48 : ((TW + 2 * kHalo + 7) / 16) * 16 + 8;
 	static constexpr int PH = TH + 2 * kHalo;
 	static constexpr int ELEMS = PW * PH;
 };
