@@ -72,6 +72,15 @@ __device__ __forceinline__ float rcpf(float x) { float r; asm("rcp.approx.ftz.f3
 __device__ __forceinline__ float sqrtaf(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rsqrtaf(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// ---- packed fp32 (sm_100 FFMA2/FADD2): two independent IEEE operations per instruction, same rounding as
+// the scalar forms, half the issue slots (measured: tools/ffma2_probe.cu)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // ---- geometry helpers --------------------------------------------------------------------------
 // ComputeDepthfromPlaneHypothesis, APD.cu:206-209
 __device__ __forceinline__ float plane_depth(const RefConst &rc, const float4 pl, const float xf, const float yf) {
@@ -290,12 +299,23 @@ __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t
 			if ((my_quad >> e) & 1u) {
 				const int qd = q.ql ^ e;
 				const int x0 = pxe - 5 + 2 * (qd & 1), y0 = pye - 5 + 2 * (qd >> 1);
+				// x and y of the projective warp advance as one packed pair (same operations as src_tap)
+				const f32x2 H03 = pk2(h[0], h[3]), H14 = pk2(h[1], h[4]), H25 = pk2(h[2], h[5]), HALF = pk2(0.5f, 0.5f);
+				float yf[3]; f32x2 YF[3];
+#pragma unroll
+				for (int d = 0; d < 3; ++d) { yf[d] = (float)(y0 + 4 * d); YF[d] = pk2(yf[d], yf[d]); }
 #pragma unroll
 				for (int c = 0; c < 3; ++c) {
 					const float xf = (float)(x0 + 4 * c);
-					const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
+					const f32x2 AXY = mul2(H03, pk2(xf, xf));
+					const float az = h[6] * xf;
 #pragma unroll
-					for (int d = 0; d < 3; ++d) v[u][c * 3 + d] = src_tap(tex, lay, h, ax, ay, az, (float)(y0 + 4 * d));
+					for (int d = 0; d < 3; ++d) {
+						const f32x2 XY = add2(H25, fma2(H14, YF[d], AXY));
+						const float rz = rcpf(h[8] + fmaf(h[7], yf[d], az));
+						float tu, tv; unpk2(fma2(XY, pk2(rz, rz), HALF), tu, tv);
+						v[u][c * 3 + d] = tex2DLayered<float>(tex, tu, tv, lay);
+					}
 				}
 			}
 		}
@@ -322,21 +342,25 @@ __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t
 		// ROLL keeps the accumulation loop small for the instruction cache (two x-offsets per trip)
 #pragma unroll(ROLL ? 1 : 3)
 		for (int i2 = 0; i2 < 3; ++i2) {
+			// the two x-offsets of a trip are independent row sums: their five running sums advance in lock
+			// step as packed pairs (lo = column 2*i2, hi = column 2*i2+1)
+			const float *rb0 = base + 2 * (2 * i2), *rb1 = rb0 + 2;
+			const float *sa0 = s0 + (2 * i2) * 6 * 32, *sb0 = s2 + (2 * i2) * 6 * 32;             // column 2*i2:   quadrants 0 (j even), 2 (j odd)
+			const float *sa1 = s1 + (2 * i2 + 1) * 6 * 32, *sb1 = s3 + (2 * i2 + 1) * 6 * 32;     // column 2*i2+1: quadrants 1, 3
+			f32x2 R = 0ull, RR = 0ull, RS = 0ull, S = 0ull, SS = 0ull;
 #pragma unroll
-			for (int ii = 0; ii < 2; ++ii) {
-				NccSums r = {0.f, 0.f, 0.f, 0.f, 0.f};
-				const float *rb = base + 2 * (2 * i2 + ii);
-				const float *sa = (ii == 0 ? s0 : s1) + (2 * i2 + ii) * 6 * 32;      // quadrant = (i&1) + 2*(j&1)
-				const float *sb = (ii == 0 ? s2 : s3) + (2 * i2 + ii) * 6 * 32;
-#pragma unroll
-				for (int j = 0; j < 6; ++j) {
-					const float rp = rb[2 * j * pitch];
-					const float sp = ((j & 1) ? sb : sa)[j * 32];
-					r.r += rp; r.rr = fmaf(rp, rp, r.rr); r.rs = fmaf(rp, sp, r.rs);
-					r.s += sp; r.ss = fmaf(sp, sp, r.ss);
-				}
-				t.r += r.r; t.rr += r.rr; t.s += r.s; t.ss += r.ss; t.rs += r.rs;
+			for (int j = 0; j < 6; ++j) {
+				const f32x2 RP = pk2(rb0[2 * j * pitch], rb1[2 * j * pitch]);
+				const f32x2 SP = pk2(((j & 1) ? sb0 : sa0)[j * 32], ((j & 1) ? sb1 : sa1)[j * 32]);
+				R = add2(RP, R); RR = fma2(RP, RP, RR); RS = fma2(RP, SP, RS);
+				S = add2(SP, S); SS = fma2(SP, SP, SS);
 			}
+			float a0, a1;
+			unpk2(R, a0, a1); t.r += a0; t.r += a1;
+			unpk2(RR, a0, a1); t.rr += a0; t.rr += a1;
+			unpk2(S, a0, a1); t.s += a0; t.s += a1;
+			unpk2(SS, a0, a1); t.ss += a0; t.ss += a1;
+			unpk2(RS, a0, a1); t.rs += a0; t.rs += a1;
 		}
 		cost = ncc_cost(t, inv_w);
 	}
