@@ -783,13 +783,34 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 	const uint32_t act = bits & vw_mask(vw, S);
 	float *p = prof + tid;
 	float min_cost15 = 2.0f, best_depth = c.depth;
+	// Sweep order: the centre window first, then outwards. The classification rules (APD.cu:2092-2143) make
+	// many pixels decidable before the whole 59-entry profile exists, and the decision is the same as the
+	// reference's (which always evaluates everything):
+	//  * min_peak is the FIRST index of the cheapest local minimum ("peak"); the pixel is WEAK whenever that
+	//    peak lies farther than weak_peak_radius from the centre, costs more than 0.5, or does not exist;
+	//  * so, with c_in = cheapest peak inside the radius (needs entries 30-r-1 .. 30+r+1 only): no inside
+	//    peak, or c_in > 0.5  =>  WEAK at once; otherwise the first outside peak cheaper than c_in (left side:
+	//    not dearer, because the first index wins ties) => WEAK.
+	// Only pixels that survive all of that need the complete profile (peak count and spread).
+	const int rad = a.weak_peak_radius;
+	const int R = min(29, max(rad + 1, 5));              // centre window half-width; >= 5 covers LocalRefine's steps
+	const int nA = 2 * R + 1, nSide = 29 - R;
+	bool decided = !on14;                                // K14 outcome already known (UNKNOWN or early WEAK)
+	uint8_t early = APD_UNKNOWN;
+	float c_in = 3.0f;
 #pragma unroll 1
-	for (int k = -30; k <= 30; ++k) {
+	for (int step = 0; step < 59; ++step) {
+		const bool phaseA = step < nA;
+		const bool right = !phaseA && step < nA + nSide;
+		const int i = phaseA ? (30 - R + step) : right ? (30 + R + 1 + (step - nA)) : (30 - R - 1 - (step - nA - nSide));
+		const int k = i - 30;
+		const bool near = (k >= -5 && k <= 5);
+		const bool want14 = DO14 && !decided;
+		const bool want15 = DO15 && on15 && near;
+		if (!__any_sync(0xffffffffu, want14 || want15)) { if (phaseA) continue; else break; }
 		const float d = c.kb * rcpf(c.disp + (float)k);
 		const bool in_range = !(d < a.depth_min || d > a.depth_max);
-		const bool near = (k >= -5 && k <= 5);
-		// profile entries 0 and 60 (k = -30, +30) are never read by the peak analysis (APD.cu:2101-2110 touches 1..59)
-		const bool need = in_range && ((on14 && k > -30 && k < 30) || (on15 && near));
+		const bool need = in_range && (want14 || want15);
 		float4 t = c.pl;
 		t.w = plane_offset(rc, xf, yf, d, t.x, t.y, t.z);
 		float acc14 = 0.0f, acc15 = 0.0f;
@@ -812,16 +833,34 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 				if (DO15) { acc15 = fmaf((float)w, ncc, acc15); if (a.geom) acc15 = fmaf((float)w, a.geom_factor * g, acc15); }   // :2217-2220
 			}
 		}
-		if (DO14 && on14) {
-			float pc = 2.0f;
-			if (in_range) { pc = acc14 * inv_wn; pc = (2.0f > pc) ? pc : 2.0f; }      // OpenCV MIN(2.0f, p_cost)
-			p[(k + 30) * kSweepNT] = pc;
-		}
-		if (DO15 && on15 && near && in_range) {
+		if (want15 && in_range) {
 			const float tc = acc15 * inv_wn;
 			if (tc < min_cost15) { min_cost15 = tc; best_depth = d; }
 		}
+		if (want14) {
+			float pc = 2.0f;
+			if (in_range) { pc = acc14 * inv_wn; pc = (2.0f > pc) ? pc : 2.0f; }      // OpenCV MIN(2.0f, p_cost)
+			p[i * kSweepNT] = pc;
+			if (phaseA) {
+				if (step == nA - 1) {                    // centre window complete: cheapest peak within the radius
+					for (int j = max(2, 30 - rad); j <= min(58, 30 + rad); ++j) {
+						const float cj = p[j * kSweepNT];
+						if (p[(j - 1) * kSweepNT] > cj && p[(j + 1) * kSweepNT] > cj && cj < c_in) c_in = cj;
+					}
+					if (c_in > 0.5f) { decided = true; early = APD_WEAK; }     // none (3.0) or too dear
+				}
+			} else if (right) {
+				const int j = i - 1;                     // newly testable peak, outside the radius on the right
+				const float cj = p[j * kSweepNT];
+				if (j <= 58 && p[(j - 1) * kSweepNT] > cj && pc > cj && cj < c_in) { decided = true; early = APD_WEAK; }
+			} else {
+				const int j = i + 1;                     // outside on the left: wins ties (smaller index)
+				const float cj = p[j * kSweepNT];
+				if (j >= 2 && pc > cj && p[(j + 1) * kSweepNT] > cj && cj <= c_in) { decided = true; early = APD_WEAK; }
+			}
+		}
 	}
+	const bool full_profile = on14 && !decided;
 	if (DO15) {
 		// cost of the current depth (APD.cu:2173-2182): the compiler hoisted normal.z * depth out of the view
 		// loop there as a rounded product, so the plane offset is -((d*nz) + fma(X0,nx,X1*ny))
@@ -849,8 +888,8 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 		}
 	}
 	if (DO14 && in_img) {
-		uint8_t out = APD_UNKNOWN;
-		if (on14) {   // peak analysis, APD.cu:2092-2143
+		uint8_t out = on14 ? early : (uint8_t)APD_UNKNOWN;
+		if (full_profile) {   // peak analysis, APD.cu:2092-2143
 			int peak_count = 0, min_peak = 0; float min_cost = 2.0f;
 			unsigned long long peaks = 0ull;
 			for (int i = 2; i < 59; ++i) {
