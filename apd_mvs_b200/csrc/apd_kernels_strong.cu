@@ -477,19 +477,24 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 			const float di = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : d0);
 			float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
 			t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
+			// A hypothesis is adopted only if its depth is in range and its weighted cost is below cost_now. Costs and
+			// weights are non-negative and every partial sum is rounded monotonically, so (a) an out-of-range
+			// hypothesis and (b) one whose partial sum already reaches cost_now can never be adopted: their remaining
+			// views are not evaluated (the reference evaluates and then discards them).
+			const float d = plane_depth(rc, t, xf, yf);
+			const bool in_range = d >= a.depth_min && d <= a.depth_max;
 			float acc = 0.0f;
-			uint32_t m = wmask;
+			uint32_t m = in_range ? wmask : 0u;
 #pragma unroll 1
 			while (__any_sync(0xffffffffu, m != 0u)) {
 				const bool want = m != 0u;
 				const int v = want ? (__ffs(m) - 1) : 0;
 				m &= m - 1u;
 				const float c = NCC(v, t, want);
-				if (want) acc = fmaf((float)vw_get(vw, v), c, acc);
+				if (want) { acc = fmaf((float)vw_get(vw, v), c, acc); if (acc * inv_wn >= cost_now) m = 0u; }
 			}
 			const float tc = acc * inv_wn;
-			const float d = plane_depth(rc, t, xf, yf);
-			if (d >= a.depth_min && d <= a.depth_max && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+			if (in_range && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
 		}
 	}
 	if (!alive) return;
