@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kFullNT) k_init_planes(const Args a) {
 	using C = TileCfg<kFullTW, kFullTH>;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float *tile = reinterpret_cast<float *>(smem_raw);
-	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
+	float *patch = tile + C::ELEMS;
+	RefConst *sr = reinterpret_cast<RefConst *>(patch + (kFullNT / 32) * kPatchFloats);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
 	float *cm = reinterpret_cast<float *>(sv + a.S);          // [S][NT] costs of this pixel
 	const int tid = threadIdx.y * kFullTW + threadIdx.x;
@@ -175,29 +176,35 @@ __global__ void __launch_bounds__(kFullNT) k_init_planes(const Args a) {
 	load_tile<kFullTW, kFullTH, kFullNT>(a, tile, x0, y0, tid);
 	load_views(a, sv, sr, tid, kFullNT);
 	__syncthreads();
+	const QuadCtx qc = make_quad_ctx(patch, tid);
 	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
-	if (px >= a.W || py >= a.H) return;
+	const int lx = threadIdx.x, ly = threadIdx.y;
+	const bool alive = px < a.W && py < a.H;                 // dead lanes stay: they fetch for their quad
 	const size_t center = (size_t)py * a.W + px;
 	const RefConst &rc = *sr;
 	const float xf = (float)px, yf = (float)py;
 	const int S = a.S;
 	const float inv36 = a.inv_w[0];
 	if (FIRST) {
-		Rng rng = rng_load(a.rng, center);
-		// GenerateRandomPlaneHypothesis, APD.cu:276-282
-		const float depth = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
-		float4 pl = random_normal(rc, xf, yf, rng, depth);
-		pl.w = plane_offset(rc, xf, yf, depth, pl.x, pl.y, pl.z);
-		rng_store(a.rng, center, rng);
-		a.planes[center] = pl;
+		float4 pl = make_float4(0.f, 0.f, 1.f, 1.f);
+		if (alive) {
+			Rng rng = rng_load(a.rng, center);
+			// GenerateRandomPlaneHypothesis, APD.cu:276-282
+			const float depth = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
+			pl = random_normal(rc, xf, yf, rng, depth);
+			pl.w = plane_offset(rc, xf, yf, depth, pl.x, pl.y, pl.z);
+			rng_store(a.rng, center, rng);
+			a.planes[center] = pl;
+		}
 		// ComputeMultiViewInitialCostandSelectedViews, APD.cu:616-662
 		int valid = 0;
+#pragma unroll 1
 		for (int v = 0; v < S; ++v) {
-			const Homog Hm = make_homography(rc, sv[v], pl);
-			const float c = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, threadIdx.x, threadIdx.y, px, py, inv36);
+			const float c = ncc6_quad<4, true>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], pl), sv[v], alive, tile, C::PW, lx, ly, px, py, inv36);
 			cm[v * kFullNT + tid] = c;
 			if (c < kCostMax) valid++;
 		}
+		if (!alive) return;
 		const int top_k = min(valid, a.top_k);
 		uint32_t bits = 0u;
 		float cost = kCostMax;
@@ -222,24 +229,34 @@ __global__ void __launch_bounds__(kFullNT) k_init_planes(const Args a) {
 		a.costs[center] = cost;
 	} else {
 		// prior (world normal, depth) -> plane in the reference camera frame, APD.cu:827-832
-		const float4 in = a.planes[center];
-		const float *R = rc.cam.R;
-		float4 pl;
-		pl.x = fmaf(in.z, R[2], fmaf(in.x, R[0], in.y * R[1]));
-		pl.y = fmaf(in.z, R[5], fmaf(in.x, R[3], in.y * R[4]));
-		pl.z = fmaf(in.z, R[8], fmaf(in.x, R[6], in.y * R[7]));
-		pl.w = plane_offset(rc, xf, yf, in.w, pl.x, pl.y, pl.z);
-		a.planes[center] = pl;
-		// ComputeMultiViewInitialCost, APD.cu:664-693 (incl. the unSetBit quirk :47-50)
-		uint32_t bits = a.sel_views[center];
-		int count = 0; float sum = 0.0f;
-		for (int v = 0; v < S; ++v) {
-			if (!((bits >> v) & 1u)) continue;
-			const Homog Hm = make_homography(rc, sv[v], pl);
-			const float c = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, C::PW, threadIdx.x, threadIdx.y, px, py, inv36);
-			if (c < kCostMax) { count++; sum += c; }
-			else bits &= (0xFFFFFFFEu << v);
+		float4 pl = make_float4(0.f, 0.f, 1.f, 1.f);
+		uint32_t bits = 0u;
+		if (alive) {
+			const float4 in = a.planes[center];
+			const float *R = rc.cam.R;
+			pl.x = fmaf(in.z, R[2], fmaf(in.x, R[0], in.y * R[1]));
+			pl.y = fmaf(in.z, R[5], fmaf(in.x, R[3], in.y * R[4]));
+			pl.z = fmaf(in.z, R[8], fmaf(in.x, R[6], in.y * R[7]));
+			pl.w = plane_offset(rc, xf, yf, in.w, pl.x, pl.y, pl.z);
+			a.planes[center] = pl;
+			bits = a.sel_views[center];
 		}
+		// ComputeMultiViewInitialCost, APD.cu:664-693 (incl. the unSetBit quirk :47-50); each lane walks its own
+		// selected views in ascending order
+		int count = 0; float sum = 0.0f;
+		uint32_t m = bits & ((S >= 32) ? 0xffffffffu : ((1u << S) - 1u));
+#pragma unroll 1
+		while (__any_sync(0xffffffffu, m != 0u)) {
+			const bool want = m != 0u;
+			const int v = want ? (__ffs(m) - 1) : 0;
+			m &= m - 1u;
+			const float c = ncc6_quad<4, true>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], pl), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
+			if (want) {
+				if (c < kCostMax) { count++; sum += c; }
+				else bits &= (0xFFFFFFFEu << v);
+			}
+		}
+		if (!alive) return;
 		a.sel_views[center] = bits;
 		a.costs[center] = (count == 0) ? kCostMax : sum * rcpf((float)count);
 	}
@@ -934,7 +951,7 @@ void launch_rng_seed(cudaStream_t st, const Args &a, unsigned long long seed) {
 }
 cudaError_t launch_init_planes(cudaStream_t st, const Args &a) {
 	using C = TileCfg<kFullTW, kFullTH>;
-	const size_t smem = C::ELEMS * 4 + smem_common(a.S) + (size_t)a.S * kFullNT * 4;
+	const size_t smem = C::ELEMS * 4 + (kFullNT / 32) * kPatchFloats * 4 + smem_common(a.S) + (size_t)a.S * kFullNT * 4;
 	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
 	if (a.state == APD_FIRST_INIT) {
 		cudaFuncSetAttribute(k_init_planes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
