@@ -346,7 +346,12 @@ __device__ __forceinline__ float geom_cost_w(const Args &a, const RefConst &rc, 
 // weighted cost of one plane for a WEAK pixel over the sampled views:
 //   sum_v w_v * (ncc_deform + geom_factor * geom) (APD.cu:918-927, 960-969, 1464-1471)
 __device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float4 pl, const Anchors &an,
-                           const VW &vw, int px, int py, float inv36, float inv9) {
+                           const VW &vw, int px, int py, float inv36, float inv9, float inv_wn, float limit) {
+	// `limit`: the caller adopts the plane only if the final weighted cost is < limit. Costs, the geometric term
+	// (with geom_factor >= 0) and weights are non-negative and partial sums are rounded monotonically, so once a
+	// partial sum reaches the limit the remaining views cannot change the outcome and are skipped (limit = +inf
+	// disables this).
+	const bool prune = a.geom_factor >= 0.0f;
 	float acc = 0.0f;
 	for (int v = 0; v < a.S; ++v) {
 		const int w = vw_get(vw, v);
@@ -354,6 +359,7 @@ __device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *s
 		float c = ncc_deform(a, rc, sv[v], v, pl, an, px, py, inv36, inv9);
 		if (a.geom) c = fmaf(a.geom_factor, geom_cost_w(a, rc, sv[v], v + 1, pl, (float)px, (float)py), c);
 		acc = fmaf((float)w, c, acc);
+		if (prune && acc * inv_wn >= limit) break;
 	}
 	return acc;
 }
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 	}
 
 	float4 pl_now = a.planes[center];
-	float cost_now = weak_cost(a, rc, sv, pl_now, an, vw, px, py, inv36, inv9) * inv_wn;
+	float cost_now = weak_cost(a, rc, sv, pl_now, an, vw, px, py, inv36, inv9, inv_wn, __int_as_float(0x7f800000)) * inv_wn;
 	const float cost_stored = cost_now;
 	float depth_now = plane_depth(rc, pl_now, xf, yf);
 	if ((flags >> best_k) & 1u) {
@@ -489,9 +495,11 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 		const float4 fit = a.fit_planes[center];
 		if (!(fit.x == 0.0f && fit.y == 0.0f && fit.z == 0.0f)) {
 			{
-				const float tc = weak_cost(a, rc, sv, fit, an, vw, px, py, inv36, inv9) * inv_wn;
 				const float d = plane_depth(rc, fit, xf, yf);
-				if (d >= a.depth_min && d <= a.depth_max && tc < cost_now) { depth_now = d; pl_now = fit; cost_now = tc; }
+				if (d >= a.depth_min && d <= a.depth_max) {      // an out-of-range plane is never adopted: not evaluated
+					const float tc = weak_cost(a, rc, sv, fit, an, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
+					if (tc < cost_now) { depth_now = d; pl_now = fit; cost_now = tc; }
+				}
 			}
 			const float depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
 			const float4 n_rand = random_normal(rc, xf, yf, rng, depth_now);
@@ -505,9 +513,11 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 				const float di = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : d0);
 				float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
 				t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
-				const float tc = weak_cost(a, rc, sv, t, an, vw, px, py, inv36, inv9) * inv_wn;
 				const float d = plane_depth(rc, t, xf, yf);
-				if (d >= a.depth_min && d <= a.depth_max && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+				if (d >= a.depth_min && d <= a.depth_max) {
+					const float tc = weak_cost(a, rc, sv, t, an, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
+					if (tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+				}
 			}
 		}
 	}
