@@ -271,17 +271,44 @@ __device__ __forceinline__ float ncc_strong(cudaTextureObject_t tex, int layer, 
 // T*32 + (lane ^ quadrant(T)): both conflict-free.
 // All four lanes of a quad must call this convergently; `want` = false lanes only help.
 constexpr int kPatchFloats = 36 * 32;            // per warp
-struct QuadCtx { float *slab; unsigned qmask; int lane, ql; };
+struct QuadCtx {
+	float *slab; unsigned qmask; int lane, ql;
+	float ref_r, ref_rr;        // the pixel's own reference-patch sums (independent of view and plane): set_ref_sums
+	bool qx, qy;                // quadrant bits of this lane
+};
 __device__ __forceinline__ QuadCtx make_quad_ctx(float *patch_base, int tid) {
 	QuadCtx q; q.slab = patch_base + (tid >> 5) * kPatchFloats; q.lane = tid & 31; q.ql = tid & 3; q.qmask = 0xFu << (q.lane & ~3);
+	q.ref_r = 0.f; q.ref_rr = 0.f;
+	q.qx = (q.ql & 1) != 0; q.qy = (q.ql & 2) != 0;
 	return q;
+}
+// Sum and sum of squares of the 6x6 reference patch in exactly the order ncc6_quad / the reference accumulate them
+// (APD.cu:556-590): they do not depend on the source view or the plane, so a pixel computes them once.
+__device__ __forceinline__ void set_ref_sums(QuadCtx &q, const float *tile, int pitch, int lx, int ly) {
+	const float *base = tile + (ly + kHalo) * pitch + (lx + kHalo) - 5 * pitch - 5;
+	float r = 0.f, rr = 0.f;
+#pragma unroll 1
+	for (int i2 = 0; i2 < 3; ++i2) {
+		const float *rb0 = base + 2 * (2 * i2), *rb1 = rb0 + 2;
+		f32x2 R = 0ull, RR = 0ull;
+#pragma unroll
+		for (int j = 0; j < 6; ++j) {
+			const f32x2 RP = pk2(rb0[2 * j * pitch], rb1[2 * j * pitch]);
+			R = add2(RP, R); RR = fma2(RP, RP, RR);
+		}
+		float a0, a1;
+		unpk2(R, a0, a1); r += a0; r += a1;
+		unpk2(RR, a0, a1); rr += a0; rr += a1;
+	}
+	q.ref_r = r; q.ref_rr = rr;
 }
 
 template <int SPT = 4, bool ROLL = true>
 __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc, bool want,
                                            const float *tile, int pitch, int lx, int ly, int px, int py, float inv_w) {
 	// must be called by all 32 lanes of the warp convergently
-	const bool active = want && centre_inside(Hm, vc, (float)px, (float)py);
+	const float pxf = (float)px, pyf = (float)py;
+	const bool active = want && centre_inside(Hm, vc, pxf, pyf);
 	const unsigned ballot = __ballot_sync(0xffffffffu, active);
 	const unsigned my_quad = (ballot >> (q.lane & ~3)) & 0xFu;      // which of my quad's four evaluation slots are live
 	// SPT evaluation slots per trip: 9*SPT fetches are in flight before any result is consumed.
@@ -295,26 +322,29 @@ __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t
 			float h[9];
 #pragma unroll
 			for (int i = 0; i < 9; ++i) h[i] = __shfl_sync(0xffffffffu, Hm.h[i], e, 4);
-			const int pxe = __shfl_sync(0xffffffffu, px, e, 4), pye = __shfl_sync(0xffffffffu, py, e, 4), lay = __shfl_sync(0xffffffffu, layer, e, 4);
+			// tap coordinates are small integers: float sums of them are exact, no conversions per tap
+			const float pxe = __shfl_sync(0xffffffffu, pxf, e, 4), pye = __shfl_sync(0xffffffffu, pyf, e, 4);
+			const int lay = __shfl_sync(0xffffffffu, layer, e, 4);
 			if ((my_quad >> e) & 1u) {
-				const int qd = q.ql ^ e;
-				const int x0 = pxe - 5 + 2 * (qd & 1), y0 = pye - 5 + 2 * (qd >> 1);
+				const float x0 = pxe + ((q.qx != ((e & 1) != 0)) ? -3.f : -5.f), y0 = pye + ((q.qy != ((e & 2) != 0)) ? -3.f : -5.f);
 				// x and y of the projective warp advance as one packed pair (same operations as src_tap)
-				const f32x2 H03 = pk2(h[0], h[3]), H14 = pk2(h[1], h[4]), H25 = pk2(h[2], h[5]), HALF = pk2(0.5f, 0.5f);
+				const f32x2 H03 = pk2(h[0], h[3]), H14 = pk2(h[1], h[4]), H25 = pk2(h[2], h[5]);
 				float yf[3]; f32x2 YF[3];
 #pragma unroll
-				for (int d = 0; d < 3; ++d) { yf[d] = (float)(y0 + 4 * d); YF[d] = pk2(yf[d], yf[d]); }
+				for (int d = 0; d < 3; ++d) { yf[d] = y0 + (float)(4 * d); YF[d] = pk2(yf[d], yf[d]); }
 #pragma unroll
 				for (int c = 0; c < 3; ++c) {
-					const float xf = (float)(x0 + 4 * c);
+					const float xf = x0 + (float)(4 * c);
 					const f32x2 AXY = mul2(H03, pk2(xf, xf));
 					const float az = h[6] * xf;
 #pragma unroll
 					for (int d = 0; d < 3; ++d) {
 						const f32x2 XY = add2(H25, fma2(H14, YF[d], AXY));
 						const float rz = rcpf(h[8] + fmaf(h[7], yf[d], az));
-						float tu, tv; unpk2(fma2(XY, pk2(rz, rz), HALF), tu, tv);
-						v[u][c * 3 + d] = tex2DLayered<float>(tex, tu, tv, lay);
+						// scalar here: the texture instruction wants (layer, x, y) in consecutive registers, which a
+						// packed result (even/odd pair) can only reach through extra moves
+						float xs, ys; unpk2(XY, xs, ys);
+						v[u][c * 3 + d] = tex2DLayered<float>(tex, fmaf(xs, rz, 0.5f), fmaf(ys, rz, 0.5f), lay);
 					}
 				}
 			}
@@ -336,7 +366,7 @@ __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t
 	__syncwarp();
 	float cost = kCostMax;
 	if (active) {
-		NccSums t = {0.f, 0.f, 0.f, 0.f, 0.f};
+		NccSums t = {q.ref_r, q.ref_rr, 0.f, 0.f, 0.f};
 		const float *base = tile + (ly + kHalo) * pitch + (lx + kHalo) - 5 * pitch - 5;
 		const float *s0 = q.slab + q.lane, *s1 = q.slab + (q.lane ^ 1), *s2 = q.slab + (q.lane ^ 2), *s3 = q.slab + (q.lane ^ 3);
 		// ROLL keeps the accumulation loop small for the instruction cache (two x-offsets per trip)
@@ -347,17 +377,15 @@ __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t
 			const float *rb0 = base + 2 * (2 * i2), *rb1 = rb0 + 2;
 			const float *sa0 = s0 + (2 * i2) * 6 * 32, *sb0 = s2 + (2 * i2) * 6 * 32;             // column 2*i2:   quadrants 0 (j even), 2 (j odd)
 			const float *sa1 = s1 + (2 * i2 + 1) * 6 * 32, *sb1 = s3 + (2 * i2 + 1) * 6 * 32;     // column 2*i2+1: quadrants 1, 3
-			f32x2 R = 0ull, RR = 0ull, RS = 0ull, S = 0ull, SS = 0ull;
+			f32x2 RS = 0ull, S = 0ull, SS = 0ull;
 #pragma unroll
 			for (int j = 0; j < 6; ++j) {
 				const f32x2 RP = pk2(rb0[2 * j * pitch], rb1[2 * j * pitch]);
 				const f32x2 SP = pk2(((j & 1) ? sb0 : sa0)[j * 32], ((j & 1) ? sb1 : sa1)[j * 32]);
-				R = add2(RP, R); RR = fma2(RP, RP, RR); RS = fma2(RP, SP, RS);
+				RS = fma2(RP, SP, RS);
 				S = add2(SP, S); SS = fma2(SP, SP, SS);
 			}
 			float a0, a1;
-			unpk2(R, a0, a1); t.r += a0; t.r += a1;
-			unpk2(RR, a0, a1); t.rr += a0; t.rr += a1;
 			unpk2(S, a0, a1); t.s += a0; t.s += a1;
 			unpk2(SS, a0, a1); t.ss += a0; t.ss += a1;
 			unpk2(RS, a0, a1); t.rs += a0; t.rs += a1;

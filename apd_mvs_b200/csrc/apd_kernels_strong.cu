@@ -176,9 +176,10 @@ __global__ void __launch_bounds__(kFullNT) k_init_planes(const Args a) {
 	load_tile<kFullTW, kFullTH, kFullNT>(a, tile, x0, y0, tid);
 	load_views(a, sv, sr, tid, kFullNT);
 	__syncthreads();
-	const QuadCtx qc = make_quad_ctx(patch, tid);
+	QuadCtx qc = make_quad_ctx(patch, tid);
 	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
 	const int lx = threadIdx.x, ly = threadIdx.y;
+	set_ref_sums(qc, tile, C::PW, lx, ly);
 	const bool alive = px < a.W && py < a.H;                 // dead lanes stay: they fetch for their quad
 	const size_t center = (size_t)py * a.W + px;
 	const RefConst &rc = *sr;
@@ -305,9 +306,10 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 	load_views(a, sv, sr, tid, NT);
 	__syncthreads();
 	tma_load_tile(&tmap, tile, &tile_bar, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, C::ELEMS * 4, tid, 0);
-	const QuadCtx qc = make_quad_ctx(xchg, tid);
+	QuadCtx qc = make_quad_ctx(xchg, tid);
 	int px, py, lx, ly;
 	half_pixel(tid, x0, y0, color, px, py, lx, ly);
+	set_ref_sums(qc, tile, C::PW, lx, ly);
 	const int W = a.W, H = a.H, S = a.S;
 	const int center = py * W + px;
 	// threads without a pixel to update stay: their lanes still fetch for the other lanes of their quad
@@ -781,9 +783,10 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 	load_views(a, sv, sr, tid, kSweepNT);
 	__syncthreads();
 	tma_load_tile(&tmap, tile, &tile_bar, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, C::ELEMS * 4, tid, 0);
-	const QuadCtx qc = make_quad_ctx(patch, tid);
+	QuadCtx qc = make_quad_ctx(patch, tid);
 	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
 	const int lx = threadIdx.x, ly = threadIdx.y;
+	set_ref_sums(qc, tile, C::PW, lx, ly);
 	const bool in_img = px < a.W && py < a.H;
 	const size_t center = (size_t)py * a.W + px;
 	const RefConst &rc = *sr;
