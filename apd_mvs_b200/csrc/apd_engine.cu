@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cstdio>
 #include "apd_device.cuh"
+#include "apd_engine_internal.h"
 
 namespace apd {
 void launch_setup_views(cudaStream_t, const apd_camera *, int, ViewConst *, RefConst *, float *);
@@ -34,31 +35,6 @@ cudaError_t launch_weak(cudaStream_t, const Args &, int iter, int color);
 
 using namespace apd;
 
-struct apd_engine {
-	int device = 0, W = 0, H = 0, N = 0, S = 0;
-	size_t npx = 0;
-	apd_params params;
-	uint64_t seed = 0;
-	cudaStream_t stream = nullptr;
-	cudaArray_t img_arr = nullptr, depth_arr = nullptr;
-	cudaTextureObject_t img_tex = 0, depth_tex = 0;
-	float *ref_lin = nullptr, *ref_pad = nullptr;
-	int ref_pitch = 0, ref_rows = 0;
-	apd_camera *d_cams = nullptr; ViewConst *d_views = nullptr; RefConst *d_ref = nullptr; float *d_invw = nullptr;
-	float4 *planes = nullptr, *fit_planes = nullptr, *prior_planes = nullptr;
-	float *costs = nullptr;
-	uint32_t *sel_views = nullptr, *prior_views = nullptr;
-	uint8_t *states = nullptr, *prior_states = nullptr, *reliable = nullptr;
-	uint2 *rng = nullptr; uint4 *view_w = nullptr;
-	short2 *anchors = nullptr, *nearest = nullptr;
-	float *scratch = nullptr;
-	CUtensorMap tmap_strong, tmap_sweep;
-	bool have_images = false, have_cams = false, have_depths = false, have_planes = false, have_states = false;
-	std::vector<cudaEvent_t> events;
-	std::vector<float> stage_ms;
-	int launches = 0, stages_run = 0;
-	std::string err;
-};
 
 static thread_local std::string g_null_err = "null handle";
 
@@ -107,7 +83,7 @@ extern "C" int apd_create(apd_handle *out, int device, int width, int height, in
 	if (width < 16 || height < 16 || width > 32767 || height > 32767) return APD_E_LIMIT;   // anchors are short2 (APD.h:48)
 	if (num_images < 2 || num_images > APD_MAX_IMAGES) return APD_E_LIMIT;                   // APD.cpp:428-431
 	apd_engine *h = new apd_engine();
-	h->device = device; h->W = width; h->H = height; h->N = num_images; h->S = num_images - 1;
+	h->device = device; h->W = width; h->H = height; h->N = num_images; h->S = num_images - 1; h->capacity = num_images;
 	h->npx = (size_t)width * height; h->seed = seed; h->params = *params; h->params.num_images = num_images;
 	int rc = check_params(h, params);
 	if (rc != APD_OK) { delete h; return rc; }
@@ -173,6 +149,14 @@ extern "C" int apd_set_params(apd_handle h, const apd_params *p) {
 }
 extern "C" int apd_set_seed(apd_handle h, uint64_t seed) { if (!h) return APD_E_ARG; h->seed = seed; return APD_OK; }
 
+extern "C" int apd_set_num_images(apd_handle h, int num_images) {
+	if (!h) return APD_E_ARG;
+	if (num_images < 2 || num_images > h->capacity) return fail(h, APD_E_LIMIT, "num_images must be 2..the count given to apd_create");
+	if (num_images != h->N) { h->have_images = h->have_cams = h->have_depths = false; }
+	h->N = num_images; h->S = num_images - 1; h->params.num_images = num_images;
+	return APD_OK;
+}
+
 extern "C" int apd_set_cameras(apd_handle h, const apd_camera *cams) {
 	if (!h || !cams) return APD_E_ARG;
 	CKH(cudaSetDevice(h->device));
@@ -191,14 +175,14 @@ static int copy_stack(apd_handle h, cudaArray_t arr, const float *const *host_im
 		p.srcPtr = make_cudaPitchedPtr((void *)src, pitch, h->W, h->H);
 		p.dstArray = arr; p.dstPos = make_cudaPos(0, 0, i);
 		p.extent = make_cudaExtent(h->W, h->H, 1);
-		p.kind = host_imgs ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+		p.kind = cudaMemcpyDefault;      // host or device pointers (unified addressing)
 		CKH(cudaMemcpy3DAsync(&p, h->stream));
 	}
 	return APD_OK;
 }
 
 static int finish_images(apd_handle h, const float *img0, size_t pitch, bool host) {
-	CKH(cudaMemcpy2DAsync(h->ref_lin, (size_t)h->W * 4, img0, pitch, (size_t)h->W * 4, h->H, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+	CKH(cudaMemcpy2DAsync(h->ref_lin, (size_t)h->W * 4, img0, pitch, (size_t)h->W * 4, h->H, cudaMemcpyDefault, h->stream));
 	launch_pad_ref(h->stream, h->ref_lin, h->W, h->H, h->W, h->ref_pad, h->ref_pitch, h->ref_rows);
 	CKH(cudaGetLastError());
 	CKH(cudaStreamSynchronize(h->stream));
@@ -248,12 +232,12 @@ extern "C" int apd_set_priors(apd_handle h, const float *planes, const uint32_t 
 	const size_t n = h->npx;
 	if (planes) {
 		if (!views) return fail(h, APD_E_ARG, "planes need views (APD.cpp:552-581)");
-		CKH(cudaMemcpyAsync(h->prior_planes, planes, n * 16, cudaMemcpyHostToDevice, h->stream));
-		CKH(cudaMemcpyAsync(h->prior_views, views, n * 4, cudaMemcpyHostToDevice, h->stream));
+		CKH(cudaMemcpyAsync(h->prior_planes, planes, n * 16, cudaMemcpyDefault, h->stream));
+		CKH(cudaMemcpyAsync(h->prior_views, views, n * 4, cudaMemcpyDefault, h->stream));
 		h->have_planes = true;
 	}
 	if (states) {
-		CKH(cudaMemcpyAsync(h->prior_states, states, n, cudaMemcpyHostToDevice, h->stream));
+		CKH(cudaMemcpyAsync(h->prior_states, states, n, cudaMemcpyDefault, h->stream));
 		h->have_states = true;
 	}
 	CKH(cudaStreamSynchronize(h->stream));

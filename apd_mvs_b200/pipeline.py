@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference's driver loop (main.cpp:140-217) on top of the scene layer of
+libapd_b200.so (include/apd_scene.h): all views, pyramid levels and per-view results stay on the GPU across the
+4 * round_num passes. Thin ctypes calls only; no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import engine as E
+from .scene import CAMERA_DTYPE
+
+
+def _bind(lib):
+    if getattr(lib, "_scene_bound", False):
+        return lib
+    vp, ci = C.c_void_p, C.c_int
+    lib.apd_scene_create.argtypes = [C.POINTER(vp), ci, ci, ci, ci, C.c_uint64]
+    lib.apd_scene_destroy.argtypes = [vp]; lib.apd_scene_destroy.restype = None
+    lib.apd_scene_last_error.argtypes = [vp]; lib.apd_scene_last_error.restype = C.c_char_p
+    lib.apd_scene_set_view.argtypes = [vp, ci, vp, C.c_size_t, vp]
+    lib.apd_scene_add_problem.argtypes = [vp, ci, C.POINTER(ci), ci]
+    lib.apd_scene_num_rounds.argtypes = [vp]
+    lib.apd_scene_round_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+    lib.apd_scene_pass_params.argtypes = [vp, ci, ci, C.POINTER(E.PatchMatchParams)]
+    lib.apd_scene_run.argtypes = [vp]
+    lib.apd_scene_run_pass.argtypes = [vp, ci, ci]
+    lib.apd_scene_run_problem.argtypes = [vp, ci, ci, ci]
+    lib.apd_scene_result_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+    for name in ("depth", "normal", "states", "views"):
+        getattr(lib, "apd_scene_get_" + name).argtypes = [vp, ci, vp]
+    lib.apd_scene_get_scaled_image.argtypes = [vp, ci, ci, vp]
+    lib.apd_scene_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib._scene_bound = True
+    return lib
+
+
+class Scene:
+    """One dense_folder of the reference: images + cameras of all views and the pair list."""
+
+    def __init__(self, images, cameras, pairs, seed: int = 1234567, device: int = 0):
+        """images: [n_views, H, W] float32 (numpy, or a torch CUDA tensor on `device`); cameras: CAMERA_DTYPE[n_views];
+        pairs: list of (ref_view, [src_views...]) in pair.txt order."""
+        self.L = _bind(E.lib())
+        n, H, W = images.shape
+        self.n_views, self.H, self.W = int(n), int(H), int(W)
+        self._h = C.c_void_p(None)
+        rc = self.L.apd_scene_create(C.byref(self._h), device, self.n_views, self.W, self.H, seed)
+        if rc:
+            raise E.ApdError(f"apd_scene_create failed ({rc})")
+        cams = np.ascontiguousarray(cameras, dtype=CAMERA_DTYPE)
+        for v in range(self.n_views):
+            if isinstance(images, np.ndarray):
+                img = np.ascontiguousarray(images[v], dtype=np.float32)
+                ptr = img.ctypes.data
+            else:
+                img = images[v].contiguous()
+                ptr = img.data_ptr()
+            self._ck(self.L.apd_scene_set_view(self._h, v, C.c_void_p(ptr), W * 4, C.c_void_p(cams[v:v + 1].ctypes.data)))
+        self.pairs = [(int(r), [int(x) for x in s]) for r, s in pairs]
+        for r, s in self.pairs:
+            arr = (C.c_int * len(s))(*s)
+            self._ck(self.L.apd_scene_add_problem(self._h, r, arr, len(s)))
+
+    # ---- main.cpp vocabulary
+    def ComputeRoundNum(self) -> int:  # main.cpp:72-88
+        return self.L.apd_scene_num_rounds(self._h)
+
+    def RoundSize(self, round_: int):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.L.apd_scene_round_size(self._h, round_, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def PassParams(self, round_: int, pass_: int) -> E.PatchMatchParams:  # main.cpp:171-211
+        p = E.PatchMatchParams()
+        self._ck(self.L.apd_scene_pass_params(self._h, round_, pass_, C.byref(p)))
+        return p
+
+    def Run(self):  # main.cpp:168-217
+        self._ck(self.L.apd_scene_run(self._h))
+
+    def RunPass(self, round_: int, pass_: int):
+        self._ck(self.L.apd_scene_run_pass(self._h, round_, pass_))
+
+    def ProcessProblem(self, round_: int, pass_: int, problem: int):  # main.cpp:91-138
+        self._ck(self.L.apd_scene_run_problem(self._h, round_, pass_, problem))
+
+    # ---- results (depths.dmb, normals.dmb, weak.bin, selected_views.bin of a view)
+    def ResultSize(self, view: int):
+        w, h = C.c_int(), C.c_int()
+        self._ck(self.L.apd_scene_result_size(self._h, view, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def _get(self, name, view, shape_tail, dtype):
+        w, h = self.ResultSize(view)
+        out = np.empty((h, w) + shape_tail, dtype=dtype)
+        self._ck(getattr(self.L, "apd_scene_get_" + name)(self._h, view, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def Depth(self, view): return self._get("depth", view, (), np.float32)
+    def Normal(self, view): return self._get("normal", view, (3,), np.float32)
+    def States(self, view): return self._get("states", view, (), np.uint8)
+    def SelectedViews(self, view): return self._get("views", view, (), np.uint32)
+
+    def ScaledImage(self, round_: int, view: int):
+        w, h = self.RoundSize(round_)
+        out = np.empty((h, w), np.float32)
+        self._ck(self.L.apd_scene_get_scaled_image(self._h, round_, view, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def Timing(self):
+        pm, wall, n = C.c_double(), C.c_double(), C.c_longlong()
+        self.L.apd_scene_get_timing(self._h, C.byref(pm), C.byref(wall), C.byref(n))
+        return {"patchmatch_ms": pm.value, "wall_ms": wall.value, "launches": n.value}
+
+    def close(self):
+        if self._h:
+            self.L.apd_scene_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise E.ApdError(f"libapd_b200 scene error {rc}: {self.L.apd_scene_last_error(self._h).decode()}")
+
+
+def ring_pairs(n_views: int, n_src: int):
+    """pair.txt of a ring of views: every view is a reference, its sources are the next n_src views."""
+    return [(r, [(r + k) % n_views for k in range(1, n_src + 1)]) for r in range(n_views)]

@@ -96,11 +96,15 @@ const char *apd_last_error(apd_handle h);
  * state / geom_consistency / weak_peak_radius / ransac_threshold / rotate_time per pass). */
 int apd_set_params(apd_handle h, const apd_params *params);
 int apd_set_seed(apd_handle h, uint64_t seed);
+/* Use fewer images than the handle was created for (problems of one scene have different numbers of source
+ * views, main.cpp:36-46); images, cameras and depths must be set again afterwards. */
+int apd_set_num_images(apd_handle h, int num_images);
 
 /* cams[num_images]; index 0 is the reference view (APD.cpp:633-634). */
 int apd_set_cameras(apd_handle h, const apd_camera *cams);
-/* images[num_images]: host pointers to float32 grey images (0..255), all width x height,
- * rows `pitch_bytes` apart (APD.cpp:588-606). */
+/* images[num_images]: pointers to float32 grey images (0..255), all width x height, rows `pitch_bytes` apart
+ * (APD.cpp:588-606). The pointers of apd_set_images / apd_set_depths / apd_set_priors may be host OR device
+ * memory of the handle's device (unified addressing decides). */
 int apd_set_images(apd_handle h, const float *const *images, size_t pitch_bytes);
 /* Same, from ONE device buffer holding the num_images images back to back
  * (image i at dev_stack + i*image_stride_bytes). Used when the image stack already lives

@@ -14,17 +14,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "apd_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(apd_[a-z_]+)\s*\(", src)))
+    names = set()
+    for hdr in ("apd_b200.h", "apd_scene.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(apd_[a-z_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_exported():
     lib = C.CDLL(E.LIB_PATH)
     names = declared_symbols()
-    assert len(names) >= 25
+    assert len(names) >= 44
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/apd_b200.h but not exported"
+        assert hasattr(lib, n), f"{n} declared in include/*.h but not exported"
 
 
 def test_struct_layouts_match_reference():

@@ -1,0 +1,131 @@
+"""GPU parity of the scene layer (include/apd_scene.h: pass scheduler + persistent device cache) against the
+reference's driver loop restated around the unmodified reference PatchMatch (oracle/ref_pipeline.py +
+oracle/_ref/libapd_ref.so). Single-GPU, pair-list order, so every (problem, pass) sees exactly the inputs it sees
+in the reference and the whole 4*round_num-pass pipeline must come out bit-identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import parity_tools as T
+from apd_mvs_b200 import engine as E
+from apd_mvs_b200 import pipeline as P
+from apd_mvs_b200.scene import make_scene
+from oracle import ref_pipeline as RP
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_available():
+    from oracle import ref_binding
+    return ref_binding.available()
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def run_reference_patchmatch(images, cams, params, depths, planes, views, states, seed):
+    from oracle.ref_binding import RefAPD
+    ref = RefAPD(images, cams, T.clone_params(params), depths=depths, planes=planes, views=views, states=states, seed=seed)
+    ref.run()
+    out = ref.outputs()
+    ref.close()
+    return out
+
+
+def make_views(W, H, n_views):
+    sc = make_scene(W, H, n_views - 1, device="cuda")
+    return sc["images"].cpu().numpy(), sc["cameras"]
+
+
+@pytest.mark.parametrize("W,H", [(1041, 781), (1040, 780)])
+def test_scaled_images_bit_exact(W, H):
+    images, cams = make_views(W, H, 3)
+    sc = P.Scene(images, cams, P.ring_pairs(3, 2))
+    assert sc.ComputeRoundNum() == RP.compute_round_num(W, H) == 2
+    assert sc.RoundSize(0) == RP.scaled_size(W, H, 2) and sc.RoundSize(1) == (W, H)
+    for v in range(3):
+        w, h = sc.RoundSize(0)
+        assert np.array_equal(bits(sc.ScaledImage(0, v)), bits(RP.resize_linear(images[v], w, h)))
+        assert np.array_equal(bits(sc.ScaledImage(1, v)), bits(images[v]))
+    sc.close()
+
+
+def test_pass_params_match_schedule():
+    images, cams = make_views(64, 48, 2)
+    big = np.zeros((2, 48, 4200), np.float32)       # 4200 px wide -> 4 rounds; only the schedule is queried
+    cams_big = cams.copy(); cams_big["width"] = 4200
+    sc = P.Scene(big, cams_big, [(0, [1])])
+    assert sc.ComputeRoundNum() == 4
+    for i in range(4):
+        for ps in range(4):
+            a, b = sc.PassParams(i, ps), RP.pass_params(E.default_params, i, ps)
+            for f in ("max_iterations", "top_k", "geom_consistency", "use_APD", "weak_peak_radius", "rotate_time", "state"):
+                assert getattr(a, f) == getattr(b, f), (i, ps, f)
+            assert np.float32(a.ransac_threshold) == np.float32(b.ransac_threshold)
+    sc.close()
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libapd_ref.so not built")
+@pytest.mark.parametrize("W,H,n_views,n_src", [(1041, 781, 3, 2), (1040, 600, 4, 3)])
+def test_whole_pipeline_bit_exact(W, H, n_views, n_src):
+    images, cams = make_views(W, H, n_views)
+    pairs = P.ring_pairs(n_views, n_src)
+    ref = RP.RefPipeline(images, cams, pairs, E.default_params, run_reference_patchmatch, seed=4242)
+    sc = P.Scene(images, cams, pairs, seed=4242)
+    assert sc.ComputeRoundNum() == ref.rounds == 2
+    for i in range(ref.rounds):
+        for ps in range(4):
+            ref.run_pass(i, ps)
+            sc.RunPass(i, ps)
+            for v in range(n_views):
+                r = ref.results[v]
+                assert sc.ResultSize(v) == (r["depth"].shape[1], r["depth"].shape[0])
+                assert np.array_equal(bits(sc.Depth(v)), bits(r["depth"])), (i, ps, v, "depth")
+                assert np.array_equal(bits(sc.Normal(v)), bits(r["normal"])), (i, ps, v, "normal")
+                assert np.array_equal(sc.States(v), r["weak"]), (i, ps, v, "states")
+                assert np.array_equal(sc.SelectedViews(v), r["views"]), (i, ps, v, "views")
+    t = sc.Timing()
+    assert t["launches"] > 0 and t["patchmatch_ms"] > 0
+    # the final maps are usable: most pixels carry an in-range depth
+    d = sc.Depth(0)
+    assert (d > 0).mean() > 0.8
+    sc.close()
+
+
+def test_run_equals_pass_by_pass():
+    images, cams = make_views(1000, 512, 3)            # one round (max size <= 1000)
+    pairs = P.ring_pairs(3, 2)
+    a = P.Scene(images, cams, pairs, seed=7)
+    b = P.Scene(images, cams, pairs, seed=7)
+    a.Run()
+    for ps in range(4):
+        b.RunPass(0, ps)
+    for v in range(3):
+        assert np.array_equal(bits(a.Depth(v)), bits(b.Depth(v)))
+        assert np.array_equal(a.States(v), b.States(v))
+    a.close(); b.close()
+
+
+def test_pass_order_is_enforced():
+    images, cams = make_views(256, 192, 3)
+    sc = P.Scene(images, cams, P.ring_pairs(3, 2))
+    with pytest.raises(E.ApdError):
+        sc.RunPass(0, 1)                                  # geometric pass before any depth map exists
+    with pytest.raises(E.ApdError):
+        sc.Depth(0)
+    sc.RunPass(0, 0)
+    assert sc.Depth(0).shape == (192, 256)
+    sc.close()
+
+
+def test_bad_arguments():
+    images, cams = make_views(64, 48, 2)
+    with pytest.raises(E.ApdError):
+        P.Scene(images, cams, [(0, [5])])                 # source view out of range
+    L = P._bind(E.lib())
+    h = C.c_void_p(None)
+    assert L.apd_scene_create(C.byref(h), 0, 1, 64, 48, 0) == -4   # APD_E_LIMIT: fewer than 2 views
+    assert L.apd_scene_run(None) == -1
