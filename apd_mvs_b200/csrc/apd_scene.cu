@@ -443,6 +443,22 @@ extern "C" int apd_scene_get_normal(apd_scene_handle s, int view, float *normal_
 	return APD_OK;
 }
 
+extern "C" int apd_scene_result_device(apd_scene_handle s, int view, void **planes, void **depth, void **states, void **views) {
+	if (!s || view < 0 || view >= s->n_views) return APD_E_ARG;
+	const ViewResult &r = s->res[view];
+	if (planes) *planes = r.planes;
+	if (depth) *depth = r.depth;
+	if (states) *states = r.states;
+	if (views) *views = r.views;
+	return APD_OK;
+}
+extern "C" int apd_scene_mark_result(apd_scene_handle s, int view, int width, int height) {
+	if (!s || view < 0 || view >= s->n_views) return APD_E_ARG;
+	if (width < 1 || height < 1 || (size_t)width * height > (size_t)s->W * s->H) return sfail(s, APD_E_ARG, "result larger than the full-resolution buffers");
+	s->res[view].W = width; s->res[view].H = height;
+	return APD_OK;
+}
+
 extern "C" int apd_scene_get_scaled_image(apd_scene_handle s, int round, int view, float *image) {
 	if (!s || !image || view < 0 || view >= s->n_views) return APD_E_ARG;
 	CKS(cudaSetDevice(s->device));

@@ -29,6 +29,8 @@ def _bind(lib):
     lib.apd_scene_result_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
     for name in ("depth", "normal", "states", "views"):
         getattr(lib, "apd_scene_get_" + name).argtypes = [vp, ci, vp]
+    lib.apd_scene_result_device.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.apd_scene_mark_result.argtypes = [vp, ci, ci, ci]
     lib.apd_scene_get_scaled_image.argtypes = [vp, ci, ci, vp]
     lib.apd_scene_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     lib._scene_bound = True
@@ -44,6 +46,7 @@ class Scene:
         self.L = _bind(E.lib())
         n, H, W = images.shape
         self.n_views, self.H, self.W = int(n), int(H), int(W)
+        self.device = device
         self._h = C.c_void_p(None)
         rc = self.L.apd_scene_create(C.byref(self._h), device, self.n_views, self.W, self.H, seed)
         if rc:
@@ -102,6 +105,30 @@ class Scene:
     def States(self, view): return self._get("states", view, (), np.uint8)
     def SelectedViews(self, view): return self._get("views", view, (), np.uint32)
 
+    # ---- multi-GPU hand-over (used by ShardedScene)
+    def depth_tensor(self, view: int, width: int, height: int):
+        """torch CUDA tensor aliasing the view's device depth buffer, shaped for a width x height result."""
+        import torch
+        d = C.c_void_p()
+        self._ck(self.L.apd_scene_result_device(self._h, view, None, C.byref(d), None, None))
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (height, width), "typestr": "<f4", "data": (d.value, False), "version": 2}
+        return torch.as_tensor(_Alias(), device=f"cuda:{self.device}")
+
+    def mark_result(self, view: int, width: int, height: int):
+        self._ck(self.L.apd_scene_mark_result(self._h, view, width, height))
+
+    def round_size(self, round_: int):
+        return self.RoundSize(round_)
+
+    def sync(self):
+        import torch
+        torch.cuda.synchronize(self.device)
+
+    def process(self, round_: int, pass_: int, problem: int):
+        self.ProcessProblem(round_, pass_, problem)
+
     def ScaledImage(self, round_: int, view: int):
         w, h = self.RoundSize(round_)
         out = np.empty((h, w), np.float32)
@@ -132,3 +159,54 @@ class Scene:
 def ring_pairs(n_views: int, n_src: int):
     """pair.txt of a ring of views: every view is a reference, its sources are the next n_src views."""
     return [(r, [(r + k) % n_views for k in range(1, n_src + 1)]) for r in range(n_views)]
+
+
+class ShardedScene:
+    """The schedule of main.cpp:168-217 over `world` ranks: problem k belongs to rank k % world; every
+    rank holds all images and cameras (one broadcast at setup) and, after each pass, the owners broadcast the depth
+    maps they produced - the only data another rank's next pass reads (geometric term, APD.cpp:492-510). Priors
+    (normals, pixel states, selected views) never leave their owner. Within a rank problems keep pair-list order, so a
+    rank sees its own earlier results of the same pass (as the reference does) and its peers' results of the previous
+    pass: the sharded schedule is block-Jacobi where the reference is Gauss-Seidel, which is why parity
+    is defined per (problem, pass) on identical inputs (oracle.ref_pipeline.RefPipeline.run_pass(world=...)).
+
+    `backend` needs process(round, pass, k), depth_tensor(view, w, h), mark_result(view, w, h), round_size(round), sync();
+    `Scene` is the GPU backend, the CPU tests use a numpy stand-in."""
+
+    def __init__(self, backend, pairs, rank: int, world: int, rounds: int):
+        self.b, self.pairs, self.rank, self.world, self.rounds = backend, pairs, rank, world, rounds
+        refs = [r for r, _ in pairs]
+        if len(set(refs)) != len(refs):
+            raise ValueError("a view may be the reference of one problem only (pair.txt has one entry per image)")
+
+    def owner(self, problem: int) -> int:
+        return problem % self.world
+
+    def my_problems(self):
+        return [k for k in range(len(self.pairs)) if self.owner(k) == self.rank]
+
+    def run_pass(self, round_: int, pass_: int):
+        for k in self.my_problems():
+            self.b.process(round_, pass_, k)
+        self.exchange(round_)
+
+    def exchange(self, round_: int):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        w, h = self.b.round_size(round_)
+        work = []
+        for k, (ref, _) in enumerate(self.pairs):
+            t = self.b.depth_tensor(ref, w, h)
+            work.append(dist.broadcast(t, src=self.owner(k), async_op=True))
+        for wk in work:
+            wk.wait()
+        self.b.sync()        # the scene's own stream must not run ahead of the collective's stream
+        for k, (ref, _) in enumerate(self.pairs):
+            if self.owner(k) != self.rank:
+                self.b.mark_result(ref, w, h)
+
+    def run(self):
+        for i in range(self.rounds):
+            for pass_ in range(4):
+                self.run_pass(i, pass_)

@@ -70,6 +70,12 @@ int apd_scene_get_depth(apd_scene_handle s, int view, float *depth);
 int apd_scene_get_normal(apd_scene_handle s, int view, float *normal_xyz);
 int apd_scene_get_states(apd_scene_handle s, int view, uint8_t *states);
 int apd_scene_get_views(apd_scene_handle s, int view, uint32_t *selected_views);
+/* Multi-GPU hand-over: device pointers of a view's result buffers (each sized for the full
+ * resolution; planes = float4 per pixel: normal xyz + depth w) so that a collective can write a peer's result in
+ * place, and the declaration that they now hold a width x height result. Ranks shard the problems; between passes
+ * only the depth maps travel (the geometric term reads the source views' depth, APD.cpp:492-510). */
+int apd_scene_result_device(apd_scene_handle s, int view, void **planes, void **depth, void **states, void **selected_views);
+int apd_scene_mark_result(apd_scene_handle s, int view, int width, int height);
 /* The round's down-scaled image of a view (what cv::resize produced in the reference), for tests. */
 int apd_scene_get_scaled_image(apd_scene_handle s, int round, int view, float *image);
 

@@ -176,9 +176,22 @@ class RefPipeline:
         st[bad] = UNKNOWN
         self.results[ref] = {"depth": depth, "normal": pl[..., :3].copy(), "weak": st, "views": vw.copy()}
 
-    def run_pass(self, i: int, pass_: int):
-        for k in range(len(self.pairs)):
-            self.process_problem(i, pass_, k)
+    def run_pass(self, i: int, pass_: int, world: int = 1):
+        """world == 1: the reference's order (every problem sees all earlier results of the same pass).
+        world > 1: what `world` ranks with round-robin problem ownership compute - a rank sees its own earlier
+        results of this pass and the other ranks' results of the previous pass (only their depth maps matter)."""
+        if world == 1:
+            for k in range(len(self.pairs)):
+                self.process_problem(i, pass_, k)
+            return
+        start = list(self.results)
+        merged = list(self.results)
+        for r in range(world):
+            self.results = list(start)
+            for k in range(r, len(self.pairs), world):
+                self.process_problem(i, pass_, k)
+                merged[self.pairs[k][0]] = self.results[self.pairs[k][0]]
+        self.results = merged
 
     def run(self):
         for i in range(self.rounds):
