@@ -168,7 +168,7 @@ class ShardedScene:
     (normals, pixel states, selected views) never leave their owner. Within a rank problems keep pair-list order, so a
     rank sees its own earlier results of the same pass (as the reference does) and its peers' results of the previous
     pass: the sharded schedule is block-Jacobi where the reference is Gauss-Seidel, which is why parity
-    is defined per (problem, pass) on identical inputs (oracle.ref_pipeline.RefPipeline.run_pass(world=...)).
+    is defined per (problem, pass) on identical inputs (the tests emulate this visibility rule around the reference).
 
     `backend` needs process(round, pass, k), depth_tensor(view, w, h), mark_result(view, w, h), round_size(round), sync();
     `Scene` is the GPU backend, the CPU tests use a numpy stand-in."""
