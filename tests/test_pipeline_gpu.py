@@ -129,3 +129,38 @@ def test_bad_arguments():
     h = C.c_void_p(None)
     assert L.apd_scene_create(C.byref(h), 0, 1, 64, 48, 0) == -4   # APD_E_LIMIT: fewer than 2 views
     assert L.apd_scene_run(None) == -1
+
+
+def test_dense_folder_command_line(tmp_path):
+    """main.cpp's command line on a synthetic dense_folder: pair.txt + JPEGs + _cam.txt in, the four result files out."""
+    cv2 = pytest.importorskip("cv2")
+    from apd_mvs_b200 import io as IO, main as M
+    W, H, V = 320, 240, 3
+    images, cams = make_views(W, H, V)
+    ids = [3, 10, 42]                                       # image ids need not be dense
+    (tmp_path / "images").mkdir(); (tmp_path / "cams").mkdir()
+    for k, image_id in enumerate(ids):
+        name = IO.ToFormatIndex(image_id)
+        cv2.imwrite(str(tmp_path / "images" / (name + ".jpg")), np.clip(images[k], 0, 255).astype(np.uint8))
+        c = cams[k]
+        R, t, K = c["R"].reshape(3, 3), c["t"], c["K"].reshape(3, 3)
+        txt = "extrinsic\n" + "".join(" ".join(repr(float(x)) for x in list(R[i]) + [t[i]]) + "\n" for i in range(3)) + "0.0 0.0 0.0 1.0\n\n"
+        txt += "intrinsic\n" + "".join(" ".join(repr(float(x)) for x in K[i]) + "\n" for i in range(3))
+        txt += f"\n{float(c['depth_min'])!r} 0.01 192 {float(c['depth_max'])!r}\n"
+        (tmp_path / "cams" / (name + "_cam.txt")).write_text(txt)
+    (tmp_path / "pair.txt").write_text("3\n3\n2 10 9.0 42 8.0\n10\n3 42 7.0 3 6.0 7 0.0\n42\n2 3 5.0 10 4.0\n")
+    assert M.main([str(tmp_path)]) == 0
+    got_ids, imgs, cams2, pairs = M.load_dense_folder(str(tmp_path))
+    assert got_ids == ids and pairs == [(0, [1, 2]), (1, [2, 0]), (2, [0, 1])]
+    assert np.array_equal(cams2["R"], cams["R"]) and np.array_equal(cams2["K"], cams["K"]) and np.array_equal(cams2["t"], cams["t"])
+    sc = P.Scene(imgs, cams2, pairs)
+    sc.Run()
+    for k, image_id in enumerate(ids):
+        out = tmp_path / "APD" / IO.ToFormatIndex(image_id)
+        d = IO.ReadBinMat(out / "depths.dmb"); n = IO.ReadBinMat(out / "normals.dmb")
+        w = IO.ReadBinMat(out / "weak.bin"); v = IO.ReadBinMat(out / "selected_views.bin")
+        assert d.shape == (H, W) and n.shape == (H, W, 3) and w.dtype == np.uint8 and v.shape == (H, W)
+        assert np.array_equal(bits(d), bits(sc.Depth(k))) and np.array_equal(bits(n), bits(sc.Normal(k)))
+        assert np.array_equal(w, sc.States(k)) and np.array_equal(v.view(np.uint32), sc.SelectedViews(k))
+        assert (d > 0).mean() > 0.7
+    sc.close()
