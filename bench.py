@@ -35,6 +35,7 @@ WORKLOADS = {
     "cfg2": (3111, 2074, 9, 3, "synthetic ETH3D-half-res shape 3111x2074, 1 ref x 9 src views, 3 iters (BASELINE.json configs[1])"),
     "cfg1": (256, 256, 1, 1, "synthetic 2-view 256x256, 1 iter (BASELINE.json configs[0])"),
     "mid": (1024, 768, 9, 3, "synthetic 1024x768, 1 ref x 9 src, 3 iters (development size)"),
+    "cfg5": (4096, 4096, 16, 8, "synthetic 4096x4096, 1 ref x 16 src views, all STRONG, 8 iters (SURVEY §8d cfg 5: strong-kernel sweep)"),
 }
 TAPS_PER_PIXEL_VIEW_ITER = 14 * 36          # 14 hypotheses x 36 taps
 ALG_BYTES_PER_TAP = 8                       # one fp32 reference sample + one fp32 source sample
