@@ -280,8 +280,61 @@ __device__ __forceinline__ float ncc_window(const Args &a, int layer, const floa
 
 struct Anchors { short2 p[APD_NEIGHBOUR_NUM]; };
 
+// The reference-image side of the nine windows of a WEAK pixel does not depend on the view or the plane: the 72 tap
+// values of the eight anchor windows and every window's sum / sum of squares (accumulated in ncc_window's order) are
+// gathered ONCE per pixel into a shared-memory column [kRefTaps + 18][kWeakNT] instead of 72 scattered global loads
+// per (hypothesis, view). The own window stays in global memory: neighbouring lanes read neighbouring addresses,
+// and shared memory spent on it would come out of the L1 that the scattered texture fetches live on.
+constexpr int kRefTaps = 8 * 9;      // anchor windows only: the own 6x6 window is read coalesced from global (L1)
+constexpr int kRefCacheRows = kRefTaps + 2 * APD_NEIGHBOUR_NUM;
+constexpr int kWeakNT = 128;
+
+template <int INC, bool STORE>
+__device__ __forceinline__ void cache_window(const Args &a, int cx, int cy, float *col, float *sums) {
+	const float *base = a.ref_pad + (size_t)(cy + kRefPad) * a.ref_pitch + (cx + kRefPad);
+	float R = 0.f, RR = 0.f;
+	int t = 0;
+#pragma unroll
+	for (int i = -5; i <= 5; i += INC) {
+		float r = 0.f, rr = 0.f;
+#pragma unroll
+		for (int j = -5; j <= 5; j += INC) {
+			const float rp = __ldg(base + (ptrdiff_t)j * a.ref_pitch + i);
+			if (STORE) col[t * kWeakNT] = rp;
+			++t;
+			r += rp; rr = fmaf(rp, rp, rr);
+		}
+		R += r; RR += rr;
+	}
+	sums[0] = R; sums[kWeakNT] = RR;
+}
+
+template <int INC, bool CACHED>
+__device__ __forceinline__ float ncc_window_cached(const Args &a, int layer, const float *h, int cx, int cy, float inv_w,
+                                                   const float *col, const float *sums) {
+	NccSums t = {sums[0], sums[kWeakNT], 0.f, 0.f, 0.f};
+	const float *base = a.ref_pad + (size_t)(cy + kRefPad) * a.ref_pitch + (cx + kRefPad);
+	int n = 0;
+#pragma unroll
+	for (int i = -5; i <= 5; i += INC) {
+		const float xf = (float)(cx + i);
+		const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
+		float rs = 0.f, ss = 0.f, sm = 0.f;
+#pragma unroll
+		for (int j = -5; j <= 5; j += INC) {
+			const float rp = CACHED ? col[n * kWeakNT] : __ldg(base + (ptrdiff_t)j * a.ref_pitch + i);
+			++n;
+			const float sp = src_tap(a.img_tex, layer, h, ax, ay, az, (float)(cy + j));
+			rs = fmaf(rp, sp, rs);
+			sm += sp; ss = fmaf(sp, sp, ss);
+		}
+		t.s += sm; t.ss += ss; t.rs += rs;
+	}
+	return ncc_cost(t, inv_w);
+}
+
 __device__ float ncc_deform(const Args &a, const RefConst &rc, const ViewConst &vc, int v, const float4 pl,
-                            const Anchors &an, int px, int py, float inv36, float inv9) {
+                            const Anchors &an, const float *rcol, int px, int py, float inv36, float inv9) {
 	const Homog Hm = make_homography(rc, vc, pl);
 	if (!centre_inside(Hm, vc, (float)px, (float)py)) return kCostMax;
 	const float *h = Hm.h;
@@ -300,8 +353,9 @@ __device__ float ncc_deform(const Args &a, const RefConst &rc, const ViewConst &
 			if ((a.sel_views[q.x + q.y * a.W] >> v) & 1u) { strong_cost += kCostMax; ++cnt; }
 			continue;
 		}
-		if (k == 0) center_cost = ncc_window<2>(a, v + 1, h, q.x, q.y, inv36);
-		else { strong_cost += ncc_window<5>(a, v + 1, h, q.x, q.y, inv9); ++cnt; }
+		const float *sums = rcol + (kRefTaps + 2 * k) * kWeakNT;
+		if (k == 0) center_cost = ncc_window_cached<2, false>(a, v + 1, h, q.x, q.y, inv36, rcol, sums);
+		else { strong_cost += ncc_window_cached<5, true>(a, v + 1, h, q.x, q.y, inv9, rcol + 9 * (k - 1) * kWeakNT, sums); ++cnt; }
 	}
 	if (cnt == 0) return center_cost;
 	strong_cost = strong_cost * rcpf((float)cnt);
@@ -345,7 +399,7 @@ __device__ __forceinline__ float geom_cost_w(const Args &a, const RefConst &rc, 
 
 // weighted cost of one plane for a WEAK pixel over the sampled views:
 //   sum_v w_v * (ncc_deform + geom_factor * geom) (APD.cu:918-927, 960-969, 1464-1471)
-__device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float4 pl, const Anchors &an,
+__device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float4 pl, const Anchors &an, const float *rcol,
                            const VW &vw, int px, int py, float inv36, float inv9, float inv_wn, float limit) {
 	// `limit`: the caller adopts the plane only if the final weighted cost is < limit. Costs, the geometric term
 	// (with geom_factor >= 0) and weights are non-negative and partial sums are rounded monotonically, so once a
@@ -356,7 +410,7 @@ __device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *s
 	for (int v = 0; v < a.S; ++v) {
 		const int w = vw_get(vw, v);
 		if (w == 0) continue;
-		float c = ncc_deform(a, rc, sv[v], v, pl, an, px, py, inv36, inv9);
+		float c = ncc_deform(a, rc, sv[v], v, pl, an, rcol, px, py, inv36, inv9);
 		if (a.geom) c = fmaf(a.geom_factor, geom_cost_w(a, rc, sv[v], v + 1, pl, (float)px, (float)py), c);
 		acc = fmaf((float)w, c, acc);
 		if (prune && acc * inv_wn >= limit) break;
@@ -364,15 +418,16 @@ __device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *s
 	return acc;
 }
 
-constexpr int kWeakNT = 128;
 constexpr int kWeakTW = 32, kWeakTH = 8;      // 128 pixels of one colour per block
 
 __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, const int color) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	RefConst *sr = reinterpret_cast<RefConst *>(smem_raw);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
-	float *cm = reinterpret_cast<float *>(sv + a.S);          // [9*S][NT]
+	float *rcache = reinterpret_cast<float *>(sv + a.S);      // [kRefCacheRows][NT] reference taps + window sums
 	const int tid = threadIdx.x;
+	// [9*S][NT] cost matrix + probabilities of this block, in the global scratch slab that stays in L1/L2
+	float *cm = a.scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (9 * a.S * kWeakNT);
 	{
 		const int nv = a.S * (int)(sizeof(ViewConst) / 4);
 		const uint32_t *g = reinterpret_cast<const uint32_t *>(a.views); uint32_t *s = reinterpret_cast<uint32_t *>(sv);
@@ -397,6 +452,15 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 #define PROB(v) cmt[(8 * S + (v)) * kWeakNT]
 	Anchors an;
 	for (int k = 0; k < APD_NEIGHBOUR_NUM; ++k) an.p[k] = a.anchors[(size_t)k * n + center];
+	float *rcol = rcache + tid;
+	cache_window<2, false>(a, an.p[0].x, an.p[0].y, rcol, rcol + kRefTaps * kWeakNT);
+#pragma unroll 1
+	for (int k = 1; k < APD_NEIGHBOUR_NUM; ++k) {
+		const short2 q = an.p[k];
+		if (q.x == -1 || q.y == -1) continue;
+		cache_window<5, true>(a, q.x, q.y, rcol + 9 * (k - 1) * kWeakNT, rcol + (kRefTaps + 2 * k) * kWeakNT);
+	}
+	const bool own_window = an.p[0].x == px && an.p[0].y == py;    // always, K3 puts the pixel itself in slot 0
 
 	// candidates = current planes of the anchors that are (still) STRONG (APD.cu:1352-1363)
 	unsigned flags = 0u; int pos[8];
@@ -408,7 +472,7 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 		if (ok) {
 			flags |= 1u << k; pos[k] = q.x + q.y * W;
 			const float4 pl = a.planes[pos[k]];
-			for (int v = 0; v < S; ++v) CM(k, v) = ncc_deform(a, rc, sv[v], v, pl, an, px, py, inv36, inv9);
+			for (int v = 0; v < S; ++v) CM(k, v) = ncc_deform(a, rc, sv[v], v, pl, an, rcol, px, py, inv36, inv9);
 		} else {
 			for (int v = 0; v < S; ++v) CM(k, v) = (k == 0 && v == 0) ? 2.0f : 0.0f;      // `= {2.0f}` quirk, APD.cu:1345
 		}
@@ -477,7 +541,7 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 	}
 
 	float4 pl_now = a.planes[center];
-	float cost_now = weak_cost(a, rc, sv, pl_now, an, vw, px, py, inv36, inv9, inv_wn, __int_as_float(0x7f800000)) * inv_wn;
+	float cost_now = weak_cost(a, rc, sv, pl_now, an, rcol, vw, px, py, inv36, inv9, inv_wn, __int_as_float(0x7f800000)) * inv_wn;
 	const float cost_stored = cost_now;
 	float depth_now = plane_depth(rc, pl_now, xf, yf);
 	if ((flags >> best_k) & 1u) {
@@ -497,7 +561,7 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 			{
 				const float d = plane_depth(rc, fit, xf, yf);
 				if (d >= a.depth_min && d <= a.depth_max) {      // an out-of-range plane is never adopted: not evaluated
-					const float tc = weak_cost(a, rc, sv, fit, an, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
+					const float tc = weak_cost(a, rc, sv, fit, an, rcol, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
 					if (tc < cost_now) { depth_now = d; pl_now = fit; cost_now = tc; }
 				}
 			}
@@ -515,7 +579,7 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 				t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
 				const float d = plane_depth(rc, t, xf, yf);
 				if (d >= a.depth_min && d <= a.depth_max) {
-					const float tc = weak_cost(a, rc, sv, t, an, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
+					const float tc = weak_cost(a, rc, sv, t, an, rcol, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
 					if (tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
 				}
 			}
@@ -534,7 +598,9 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 			if (w == 0) continue;
 			const Homog Hm = make_homography(rc, sv[v], final_plane);
 			float c = kCostMax;
-			if (centre_inside(Hm, sv[v], xf, yf)) c = ncc_window<2>(a, v + 1, Hm.h, px, py, inv36);
+			if (centre_inside(Hm, sv[v], xf, yf))
+				c = own_window ? ncc_window_cached<2, false>(a, v + 1, Hm.h, px, py, inv36, rcol, rcol + kRefTaps * kWeakNT)
+				               : ncc_window<2>(a, v + 1, Hm.h, px, py, inv36);
 			acc = fmaf((float)w, c, acc);
 		}
 		a.costs[center] = acc * inv_wn;
@@ -576,7 +642,7 @@ cudaError_t launch_fit_plane(cudaStream_t st, const Args &a) {
 	return cudaGetLastError();
 }
 cudaError_t launch_weak(cudaStream_t st, const Args &a, int iter, int color) {
-	const size_t smem = sizeof(RefConst) + (size_t)a.S * sizeof(ViewConst) + (size_t)9 * a.S * kWeakNT * 4;
+	const size_t smem = sizeof(RefConst) + (size_t)a.S * sizeof(ViewConst) + (size_t)kRefCacheRows * kWeakNT * 4;
 	if (smem > 227 * 1024) return cudaErrorInvalidValue;
 	cudaFuncSetAttribute(k_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 g((a.W + kWeakTW - 1) / kWeakTW, (a.H + kWeakTH - 1) / kWeakTH);
