@@ -175,6 +175,8 @@ class ShardedScene:
 
     def __init__(self, backend, pairs, rank: int, world: int, rounds: int):
         self.b, self.pairs, self.rank, self.world, self.rounds = backend, pairs, rank, world, rounds
+        self.process_ms = 0.0
+        self.exchange_ms = 0.0
         refs = [r for r, _ in pairs]
         if len(set(refs)) != len(refs):
             raise ValueError("a view may be the reference of one problem only (pair.txt has one entry per image)")
@@ -186,9 +188,14 @@ class ShardedScene:
         return [k for k in range(len(self.pairs)) if self.owner(k) == self.rank]
 
     def run_pass(self, round_: int, pass_: int):
+        import time
+        t0 = time.perf_counter()
         for k in self.my_problems():
             self.b.process(round_, pass_, k)
+        t1 = time.perf_counter()
         self.exchange(round_)
+        self.process_ms += 1e3 * (t1 - t0)
+        self.exchange_ms += 1e3 * (time.perf_counter() - t1)      # includes waiting for the slowest owner
 
     def exchange(self, round_: int):
         if self.world == 1:

@@ -64,6 +64,10 @@ def main():
     wall = torch.tensor([1e3 * (time.perf_counter() - t0)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    per_rank = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+    per_rank[rank, 0], per_rank[rank, 1] = sh.process_ms, sh.exchange_ms
+    if world > 1:
+        dist.all_reduce(per_rank)
     ok = torch.tensor([1], device=dev)
     if args.check:
         import parity_tools as T
@@ -93,7 +97,9 @@ def main():
     if rank == 0:
         line = {"workload": f"{V} views {W}x{H}, {S} source views each, {rounds} rounds x 4 passes", "n_gpus": world,
                 "wall_ms_max_over_ranks": round(float(wall[0]), 1), "runs_total": 4 * rounds * V,
-                "runs_per_s": round(4 * rounds * V / (float(wall[0]) * 1e-3), 2)}
+                "runs_per_s": round(4 * rounds * V / (float(wall[0]) * 1e-3), 2),
+                "per_rank_process_ms": [round(float(x), 1) for x in per_rank[:, 0]],
+                "per_rank_exchange_and_wait_ms": [round(float(x), 1) for x in per_rank[:, 1]]}
         if args.check:
             line["bit_identical_to_reference_emulation"] = bool(int(ok[0]))
         print(json.dumps(line))
