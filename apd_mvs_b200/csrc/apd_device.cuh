@@ -414,8 +414,30 @@ struct Args {
 	uint32_t *sel_views; uint8_t *states; uint2 *rng; uint4 *view_w;
 	short2 *anchors;             // [9][W*H]: slot k of pixel p at anchors[k*W*H + p] (reference: compact [weak_idx*9+k])
 	short2 *nearest; uint8_t *reliable;
-	float *scratch;              // per-block cost matrices of the propagation kernels (9*S floats per pixel of one colour)
+	float *scratch;              // slab pool for per-block work arrays (cost matrices, K14 profiles): one slab per RESIDENT block
+	int *slab_slots;             // [kSlabSMs * kSlabPerSM] 0 = free, 1 = taken
+	int slab_stride;             // floats per slab
 };
+
+// ---- slab pool: work arrays too big for shared memory (which would come out of the L1 the texture fetches live on)
+// stay in a small pool indexed by (SM, resident block), so they are rewritten in place in L1/L2 and never stream to DRAM.
+constexpr int kSlabSMs = 256, kSlabPerSM = 8;
+// Thread 0 claims a slab of its SM; the caller's next __syncthreads() publishes s_slot[0] (slab index), s_slot[1] (exit count).
+__device__ __forceinline__ void slab_acquire(const Args &a, int *s_slot, int tid) {
+	if (tid == 0) {
+		unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		const int base = (int)(smid % kSlabSMs) * kSlabPerSM;
+		int k = 0;
+		while (atomicCAS(&a.slab_slots[base + k], 0, 1) != 0) k = (k + 1) % kSlabPerSM;   // fewer resident blocks per SM than slots
+		s_slot[0] = base + k; s_slot[1] = 0;
+	}
+}
+__device__ __forceinline__ float *slab_ptr(const Args &a, const int *s_slot) { return a.scratch + (size_t)s_slot[0] * a.slab_stride; }
+// Every thread of the block calls this exactly once, after its last access to the slab; the last one frees it.
+__device__ __forceinline__ void slab_exit(const Args &a, int *s_slot, int nthreads) {
+	__threadfence_block();
+	if (atomicAdd(&s_slot[1], 1) == nthreads - 1) atomicExch(&a.slab_slots[s_slot[0]], 0);
+}
 
 // view weights: 32 nibbles (sum <= 15) in one uint4 per pixel (reference: 32 bytes, APD.cpp:645)
 struct VW { unsigned long long lo, hi; };

@@ -106,13 +106,17 @@ extern "C" int apd_create(apd_handle *out, int device, int width, int height, in
 	ALLOC(h->states, n); ALLOC(h->prior_states, n); ALLOC(h->reliable, n);
 	ALLOC(h->rng, n * 24); ALLOC(h->view_w, n * 16);
 	ALLOC(h->anchors, n * APD_NEIGHBOUR_NUM * sizeof(short2)); ALLOC(h->nearest, n * sizeof(short2));
-	{   // one [9*S][128] slab per 32x8 tile of the half-resolution launches
-		const size_t tiles = (size_t)((width + 31) / 32) * ((height + 7) / 8);
-		ALLOC(h->scratch, tiles * 9 * (size_t)h->S * 128 * 4);
+	{   // slab pool (apd_device.cuh): one slab per resident block, big enough for k_strong / k_weak's [9*S][128] cost
+		// matrices and k_sweep's [61][128] profile
+		const int rows = 9 * h->S > 61 ? 9 * h->S : 61;
+		h->slab_stride = rows * 128;
+		ALLOC(h->scratch, (size_t)kSlabSMs * kSlabPerSM * h->slab_stride * 4);
+		ALLOC(h->slab_slots, (size_t)kSlabSMs * kSlabPerSM * 4);
 	}
 #undef ALLOC
 	if (make_layered(h, &h->img_arr, &h->img_tex) != APD_OK) return bail(APD_E_CUDA);
 	if (make_tensor_maps(h->ref_pad, h->ref_pitch, h->ref_rows, &h->tmap_strong, &h->tmap_sweep) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return bail(APD_E_CUDA); }
+	cudaMemsetAsync(h->slab_slots, 0, (size_t)kSlabSMs * kSlabPerSM * 4, h->stream);
 	cudaMemsetAsync(h->costs, 0, n * 4, h->stream);
 	cudaMemsetAsync(h->view_w, 0, n * 16, h->stream);
 	cudaMemsetAsync(h->planes, 0, n * 16, h->stream);
@@ -133,7 +137,7 @@ extern "C" void apd_destroy(apd_handle h) {
 	if (h->img_arr) cudaFreeArray(h->img_arr);
 	if (h->depth_arr) cudaFreeArray(h->depth_arr);
 	void *ptrs[] = {h->ref_lin, h->ref_pad, h->d_cams, h->d_views, h->d_ref, h->d_invw, h->planes, h->fit_planes, h->prior_planes,
-	                h->costs, h->sel_views, h->prior_views, h->states, h->prior_states, h->reliable, h->rng, h->view_w, h->anchors, h->nearest, h->scratch};
+	                h->costs, h->sel_views, h->prior_views, h->states, h->prior_states, h->reliable, h->rng, h->view_w, h->anchors, h->nearest, h->scratch, h->slab_slots};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
@@ -261,7 +265,7 @@ static Args make_args(apd_handle h) {
 	a.ref_pad = h->ref_pad; a.views = h->d_views; a.ref = h->d_ref;
 	a.planes = h->planes; a.fit_planes = h->fit_planes; a.costs = h->costs;
 	a.sel_views = h->sel_views; a.states = h->states; a.rng = h->rng; a.view_w = h->view_w;
-	a.anchors = h->anchors; a.nearest = h->nearest; a.reliable = h->reliable; a.scratch = h->scratch;
+	a.anchors = h->anchors; a.nearest = h->nearest; a.reliable = h->reliable; a.scratch = h->scratch; a.slab_slots = h->slab_slots; a.slab_stride = h->slab_stride;
 	return a;
 }
 
@@ -293,6 +297,7 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 		CKH(cudaMemsetAsync(h->sel_views, 0, n * 4, st));
 	}
 	CKH(cudaMemsetAsync(h->fit_planes, 0, n * 16, st));                            // APD.cpp:651
+	CKH(cudaMemsetAsync(h->slab_slots, 0, (size_t)kSlabSMs * kSlabPerSM * 4, st));  // all slabs free
 	launch_setup_views(st, h->d_cams, h->S, h->d_views, h->d_ref, h->d_invw); h->launches++;
 	CKH(cudaGetLastError());
 

@@ -25,7 +25,7 @@ struct apd_engine {
 	uint8_t *states = nullptr, *prior_states = nullptr, *reliable = nullptr;
 	uint2 *rng = nullptr; uint4 *view_w = nullptr;
 	short2 *anchors = nullptr, *nearest = nullptr;
-	float *scratch = nullptr;
+	float *scratch = nullptr; int *slab_slots = nullptr; int slab_stride = 0;
 	CUtensorMap tmap_strong, tmap_sweep;
 	bool have_images = false, have_cams = false, have_depths = false, have_planes = false, have_states = false;
 	std::vector<cudaEvent_t> events;

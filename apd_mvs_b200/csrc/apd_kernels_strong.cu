@@ -299,12 +299,14 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 	RefConst *sr = reinterpret_cast<RefConst *>(xchg + (NT / 32) * kPatchFloats);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
 	const int tid = threadIdx.x;
-	// [9*S][NT] per block: 8xS cost matrix + S probabilities, in a global scratch slab that stays in L1/L2
-	float *cm = a.scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (9 * a.S * NT);
 	const int x0 = blockIdx.x * kHalfTW, y0 = blockIdx.y * kHalfTH;
+	int *s_slot = reinterpret_cast<int *>(&tile_bar + 1);         // 8 spare bytes behind the mbarrier
 	tma_barrier_init(&tile_bar, tid);
+	slab_acquire(a, s_slot, tid);
 	load_views(a, sv, sr, tid, NT);
 	__syncthreads();
+	// [9*S][NT] per block: 8xS cost matrix + S probabilities, in this block's slab of the L1/L2-resident pool
+	float *cm = slab_ptr(a, s_slot);
 	tma_load_tile(&tmap, tile, &tile_bar, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, C::ELEMS * 4, tid, 0);
 	QuadCtx qc = make_quad_ctx(xchg, tid);
 	int px, py, lx, ly;
@@ -516,6 +518,7 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 			if (in_range && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
 		}
 	}
+	slab_exit(a, s_slot, NT);
 	if (!alive) return;
 	rng_store(a.rng, center, rng);
 	vw_store(a.view_w, center, vw);
@@ -776,12 +779,16 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 	float *patch = tile + C::ELEMS + 4;
 	RefConst *sr = reinterpret_cast<RefConst *>(patch + (kSweepNT / 32) * kPatchFloats);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
-	float *prof = reinterpret_cast<float *>(sv + a.S);        // [61][NT] cost profile (K14)
 	const int tid = threadIdx.y * kSweepTW + threadIdx.x;
 	const int x0 = blockIdx.x * kSweepTW, y0 = blockIdx.y * kSweepTH;
+	int *s_slot = reinterpret_cast<int *>(&tile_bar + 1);         // 8 spare bytes behind the mbarrier
 	tma_barrier_init(&tile_bar, tid);
+	slab_acquire(a, s_slot, tid);
 	load_views(a, sv, sr, tid, kSweepNT);
 	__syncthreads();
+	// [61][NT] cost profile (K14) in this block's slab: 31 KB of shared memory per block would leave the texture
+	// fetches almost no L1
+	float *prof = slab_ptr(a, s_slot);
 	tma_load_tile(&tmap, tile, &tile_bar, x0 - kHalo + kRefPad, y0 - kHalo + kRefPad, C::ELEMS * 4, tid, 0);
 	QuadCtx qc = make_quad_ctx(patch, tid);
 	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
@@ -935,6 +942,7 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 		}
 		a.states[center] = out;
 	}
+	slab_exit(a, s_slot, kSweepNT);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -994,7 +1002,7 @@ cudaError_t launch_classify(cudaStream_t st, const Args &a) {
 // mode 0: K14 only, 1: K15 only, 2: K14+K15 fused
 cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode, const CUtensorMap *tmap) {
 	using C = TileCfg<kSweepTW, kSweepTH>;
-	const size_t smem = C::ELEMS * 4 + 16 + (kSweepNT / 32) * kPatchFloats * 4 + smem_common(a.S) + (size_t)61 * kSweepNT * 4;
+	const size_t smem = C::ELEMS * 4 + 16 + (kSweepNT / 32) * kPatchFloats * 4 + smem_common(a.S);
 	dim3 b(kSweepTW, kSweepTH), g((a.W + kSweepTW - 1) / kSweepTW, (a.H + kSweepTH - 1) / kSweepTH);
 	static const bool coop = getenv("APD_SWEEP_SIMPLE") == nullptr;   // cooperative fetch is the default (A/B measured: 16.9 vs 22.4 ms)
 #define SWEEP_LAUNCH(A, B, Cc) do { cudaFuncSetAttribute(k_sweep<A, B, Cc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_sweep<A, B, Cc><<<g, b, smem, st>>>(a, *tmap); } while (0)

@@ -425,9 +425,9 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 	RefConst *sr = reinterpret_cast<RefConst *>(smem_raw);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
 	float *rcache = reinterpret_cast<float *>(sv + a.S);      // [kRefCacheRows][NT] reference taps + window sums
+	int *s_slot = reinterpret_cast<int *>(rcache + kRefCacheRows * kWeakNT);
 	const int tid = threadIdx.x;
-	// [9*S][NT] cost matrix + probabilities of this block, in the global scratch slab that stays in L1/L2
-	float *cm = a.scratch + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (9 * a.S * kWeakNT);
+	slab_acquire(a, s_slot, tid);
 	{
 		const int nv = a.S * (int)(sizeof(ViewConst) / 4);
 		const uint32_t *g = reinterpret_cast<const uint32_t *>(a.views); uint32_t *s = reinterpret_cast<uint32_t *>(sv);
@@ -436,14 +436,16 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 		for (int i = tid; i < (int)(sizeof(RefConst) / 4); i += kWeakNT) srr[i] = gr[i];
 	}
 	__syncthreads();
+	// [9*S][NT] cost matrix + probabilities of this block, in its slab of the L1/L2-resident pool
+	float *cm = slab_ptr(a, s_slot);
 	const int lx = tid & 31, row = tid >> 5;                   // 4 row pairs of 32 columns
 	const int px = blockIdx.x * kWeakTW + lx;
 	const int ybase = blockIdx.y * kWeakTH + 2 * row;
 	const int py = ybase + ((px + ybase + color) & 1);
-	if (px >= a.W || py >= a.H || py >= a.half_rows) return;
+	if (px >= a.W || py >= a.H || py >= a.half_rows) { slab_exit(a, s_slot, kWeakNT); return; }
 	const int W = a.W, S = a.S; const size_t n = (size_t)W * a.H;
 	const int center = py * W + px;
-	if (a.states[center] != APD_WEAK) return;
+	if (a.states[center] != APD_WEAK) { slab_exit(a, s_slot, kWeakNT); return; }
 	const RefConst &rc = *sr;
 	const float xf = (float)px, yf = (float)py;
 	const float inv36 = a.inv_w[0], inv9 = a.inv_w[1];
@@ -605,6 +607,7 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 		}
 		a.costs[center] = acc * inv_wn;
 	}
+	slab_exit(a, s_slot, kWeakNT);
 #undef CM
 #undef PROB
 }
@@ -642,7 +645,7 @@ cudaError_t launch_fit_plane(cudaStream_t st, const Args &a) {
 	return cudaGetLastError();
 }
 cudaError_t launch_weak(cudaStream_t st, const Args &a, int iter, int color) {
-	const size_t smem = sizeof(RefConst) + (size_t)a.S * sizeof(ViewConst) + (size_t)kRefCacheRows * kWeakNT * 4;
+	const size_t smem = sizeof(RefConst) + (size_t)a.S * sizeof(ViewConst) + (size_t)kRefCacheRows * kWeakNT * 4 + 16;
 	if (smem > 227 * 1024) return cudaErrorInvalidValue;
 	cudaFuncSetAttribute(k_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 g((a.W + kWeakTW - 1) / kWeakTW, (a.H + kWeakTH - 1) / kWeakTH);
