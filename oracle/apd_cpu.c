@@ -1,7 +1,7 @@
 /*
  * oracle/apd_cpu.c — plain-C CPU restatement of the reference PatchMatch path (whoiszzj/APD-MVS,
- * APD.cu:791-2495) for pixels that are not WEAK, i.e. the whole schedule of a pass with
- * use_APD == false (main.cpp round 0) and the strong-pixel part of the later passes.
+ * APD.cu:791-2495): all 15 kernels of APD::RunPatchMatch, i.e. the strong-pixel schedule (K1, K5-K7,
+ * K11-K15) and the adaptive-patch-deformation path of WEAK pixels (K2-K4, K8-K10).
  *
  * TEST INFRASTRUCTURE ONLY. Nothing under apd_mvs_b200/ links, loads or calls this file; it is
  * used by tests/ (as the checker), by __graft_entry__.smoke() and by bench.py's cpu_baseline leg.
@@ -18,6 +18,9 @@
  * guide's linear-filtering definition (clamp addressing, 1.8 fixed-point weights).
  */
 #include <math.h>
+#ifndef M_PI
+#define M_PI 3.14159265358979323846   /* APD.h:7 */
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,6 +46,11 @@ typedef struct {
 	const Camera *cams;       /* [N] */
 	Params p;
 	f4 *planes; float *costs; uint32_t *views; uint8_t *states; uint8_t *vw; /* [H*W*32] */ Rng *rng;
+	/* deformation path (WEAK pixels) */
+	int16_t *anchors;         /* [H*W][9][2]: slot 0 = the pixel itself, (-1,-1) = absent (reference: compact weak index) */
+	int16_t *nearest;         /* [H*W][2] nearest STRONG pixel */
+	uint8_t *reliable;        /* [H*W] */
+	f4 *fit;                  /* [H*W] RANSAC plane through the anchors */
 } Ctx;
 
 /* ---- curand XORWOW (curand_kernel.h) --------------------------------------------------------- */
@@ -402,15 +410,344 @@ static void refine_pixel(Ctx *c, int px, int py) {
 	if (cn - minc > 0.1) c->planes[ctr].w = bestd;
 }
 
-/* APD::RunPatchMatch, APD.cu:2386-2495, for the launches that touch non-WEAK pixels. Returns the number
- * of stages executed; stage numbering as in include/apd_b200.h (weak-path stages are no-ops here). */
-int apd_cpu_run(int W, int H, int N, const float *images, const float *depths, const Camera *cams, const Params *params,
-                const float *prior_planes, const uint32_t *prior_views, const uint8_t *prior_states, unsigned long long seed,
-                int stage_end, float *planes, float *costs, uint32_t *views, uint8_t *states, uint8_t *view_weights, uint32_t *rng6) {
+/* =================================================================================================
+ * Adaptive patch deformation: the kernels that touch WEAK pixels.
+ * ================================================================================================= */
+#define NEIGHBOUR_NUM 9
+#define MAX_SEARCH_RADIUS 4096
+
+/* FindNearestStrongPoint, APD.cu:2234-2270 (scan order x outer, y inner; strict <) */
+static void nearest_strong_pixel(Ctx *c, int px, int py) {
+	const int W = c->W, H = c->H; const size_t ctr = (size_t)py * W + px;
+	c->nearest[2 * ctr] = -1; c->nearest[2 * ctr + 1] = -1;
+	if (c->states[ctr] != WEAK) return;
+	float min_dist = 255.0f;
+	for (int x = -100; x <= 100; ++x) for (int y = -100; y <= 100; ++y) {
+		const int nx = px + x, ny = py + y;
+		if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+		if (c->states[(size_t)ny * W + nx] == STRONG) {
+			float dist = sqrtf((float)(x * x + y * y));
+			if (dist < min_dist) { min_dist = dist; c->nearest[2 * ctr] = (int16_t)nx; c->nearest[2 * ctr + 1] = (int16_t)ny; }
+		}
+	}
+}
+
+/* NormalizeVec2, APD.cu:135-141. The FMAs below are where the reference's compiler contracts (read off its SASS);
+ * its rsqrt/sqrt are MUFU approximations, which a CPU cannot reproduce: agreement with the GPU is statistical. */
+static void normalize2(float *x, float *y) { float r = 1.0f / sqrtf(fmaf(*x, *x, *y * *y)); *x *= r; *y *= r; }
+typedef struct { float x, y, z; } f3;
+static f3 point3(const Camera *cam, int x, int y, float depth) { float X[3]; get3d(cam, (float)x, (float)y, depth, X); f3 p = {X[0], X[1], X[2]}; return p; }
+/* PointinTriangle, APD.cu:91-112 */
+static int point_in_triangle(const int16_t *A, const int16_t *B, const int16_t *C, int px, int py) {
+	float abx = (float)(B[0] - A[0]), aby = (float)(B[1] - A[1]), bcx = (float)(C[0] - B[0]), bcy = (float)(C[1] - B[1]);
+	float cax = (float)(A[0] - C[0]), cay = (float)(A[1] - C[1]);
+	float ab = sqrtf(abx * abx + aby * aby), bc = sqrtf(bcx * bcx + bcy * bcy), ca = sqrtf(cax * cax + cay * cay);
+	if (ab <= 2.0f || bc <= 2.0f || ca <= 2.0f) return 0;
+	if (!(ab + bc > ca && bc + ca > ab && ab + ca > bc)) return 0;
+	float pax = (float)(A[0] - px), pay = (float)(A[1] - py), pbx = (float)(B[0] - px), pby = (float)(B[1] - py);
+	float pcx = (float)(C[0] - px), pcy = (float)(C[1] - py);
+	float t1 = pax * pby - pay * pbx, t2 = pbx * pcy - pby * pcx, t3 = pcx * pay - pcy * pax;
+	return t1 * t2 >= 0.0f && t1 * t3 >= 0.0f;
+}
+/* unit-normal plane through three points (APD.cu:1897-1907, 2338-2349); 0 if degenerate */
+static int plane_from_points(f3 A, f3 B, f3 C, f4 *pl) {
+	float acx = A.x - C.x, acy = A.y - C.y, acz = A.z - C.z, bcx = B.x - C.x, bcy = B.y - C.y, bcz = B.z - C.z;
+	f4 n = {acy * bcz - bcy * acz, -(acx * bcz - bcx * acz), acx * bcy - bcx * acy, 0};
+	if ((n.x == 0.0f && n.y == 0.0f && n.z == 0.0f) || isnan(n.x) || isnan(n.y) || isnan(n.z)) return 0;
+	normalize3(&n);
+	n.w = -(n.x * A.x + n.y * A.y + n.z * A.z);
+	*pl = n; return 1;
+}
+static float plane_dist(f4 pl, f3 p) { return fabsf(pl.x * p.x + pl.y * p.y + pl.z * p.z + pl.w); }
+
+/* GenNeighbours, APD.cu:1750-1969: deformable anchors along 8 directions x rotate_time sub-rotations, then a
+ * 50-draw RANSAC plane through the anchors' 3-D points; the anchors are sorted by their distance to that plane. */
+static void gen_anchors_pixel(Ctx *c, int px, int py) {
+	const int W = c->W, H = c->H; const size_t ctr = (size_t)py * W + px; const Camera *rc = &c->cams[0];
+	if (c->states[ctr] != WEAK) return;
+	int16_t *an = &c->anchors[ctr * NEIGHBOUR_NUM * 2];
+	for (int k = 0; k < NEIGHBOUR_NUM * 2; ++k) an[k] = -1;
+	an[0] = (int16_t)px; an[1] = (int16_t)py;
+	Rng *r = &c->rng[ctr];
+	const int rotate_time = c->p.rotate_time;
+	const float angle = 45.0f / rotate_time;                                                  /* :1790-1795 */
+	const float cos_a = (float)cos(angle * M_PI / 180.f), sin_a = (float)sin(angle * M_PI / 180.f);
+	const float thresh = (float)cos((angle / 2.0f) * M_PI / 180.0f);
+	int shift_range = (int)(tan((angle / 2.0f) * M_PI / 180.0f) * 20); if (shift_range < 1) shift_range = 1;
+	int16_t sp[32][2]; unsigned valid = 0u; int found = 0;
+	for (int i = 0; i < 32; ++i) sp[i][0] = sp[i][1] = -1;
+	int base = -1;
+	for (int ox = -1; ox <= 1; ++ox) for (int oy = -1; oy <= 1; ++oy) {
+		if (ox == 0 && oy == 0) continue;
+		float dx = (float)ox, dy = (float)oy; normalize2(&dx, &dy);
+		++base;
+		for (int rot = 0; rot < rotate_time; ++rot) {
+			const int di = base * 4 + rot;
+			for (int radius = 2; radius <= MAX_SEARCH_RADIUS; radius = (radius * 2 < radius + 25) ? radius * 2 : radius + 25) {
+				const float tx = fmaf((float)radius, dx, (float)px), ty = fmaf((float)radius, dy, (float)py);
+				if (tx < 0.0f || ty < 0.0f || tx >= (float)W || ty >= (float)H) break;
+				for (int t = 0; t < 4; ++t) {
+					/* (curand() % 2 == 0 ? 1 : -1) * curand() % shift_range, evaluated in unsigned arithmetic (:1813-1814) */
+					const uint32_t d1 = rng_next(r), d2 = rng_next(r), d3 = rng_next(r), d4 = rng_next(r);
+					const uint32_t xs = (((d1 & 1u) == 0u) ? d2 : (0u - d2)) % (uint32_t)shift_range;
+					const uint32_t ys = (((d3 & 1u) == 0u) ? d4 : (0u - d4)) % (uint32_t)shift_range;
+					float ddx = fmaf(dx, 20.0f, (float)xs), ddy = fmaf(dy, 20.0f, (float)ys); normalize2(&ddx, &ddy);
+					int nx = (int16_t)(int)fmaf((float)radius, ddx, (float)px), ny = (int16_t)(int)fmaf((float)radius, ddy, (float)py);
+					if (nx < 6 || ny < 6 || nx >= W - 6 || ny >= H - 6) continue;
+					size_t nc = (size_t)ny * W + nx;
+					if (c->states[nc] != STRONG) {
+						const int16_t sx = c->nearest[2 * nc], sy = c->nearest[2 * nc + 1];
+						if (sx == -1 || sy == -1) continue;
+						nx = sx; ny = sy;
+					}
+					float tdx = (float)(nx - px), tdy = (float)(ny - py); normalize2(&tdx, &tdy);
+					if (fmaf(tdx, dx, tdy * dy) > thresh) { sp[di][0] = (int16_t)nx; sp[di][1] = (int16_t)ny; valid |= 1u << di; ++found; break; }
+				}
+				if ((valid >> di) & 1u) break;
+			}
+			const float rx = fmaf(dx, cos_a, -(dy * sin_a)), ry = fmaf(dx, sin_a, dy * cos_a);
+			dx = rx; dy = ry; normalize2(&dx, &dy);
+		}
+	}
+	if (found <= 3) { c->reliable[ctr] = 0; return; }
+	int16_t pts[32][2]; f3 p3[32]; int vc = 0;
+	const f3 c3 = point3(rc, px, py, c->planes[ctr].w);                 /* planes[].w still holds the prior depth here */
+	for (int i = 0; i < 32; ++i) {
+		pts[i][0] = pts[i][1] = -1;
+		if ((valid >> i) & 1u) { pts[vc][0] = sp[i][0]; pts[vc][1] = sp[i][1];
+			p3[vc] = point3(rc, sp[i][0], sp[i][1], c->planes[(size_t)sp[i][1] * W + sp[i][0]].w); ++vc; }
+	}
+	const float dd = c->p.depth_max - c->p.depth_min, thr = c->p.ransac_threshold;
+	f4 best = {0, 0, 0, 0}; int ua = -1, ub = -1, uc = -1, max_count = 3, has = 0; float min_cost = FLT_MAX;
+	for (int it = 0; it < 50; ++it) {
+		const int ia = (int)(rng_next(r) % (uint32_t)vc), ib = (int)(rng_next(r) % (uint32_t)vc), ic = (int)(rng_next(r) % (uint32_t)vc);
+		if (ia == ib || ib == ic || ia == ic) continue;
+		if (!point_in_triangle(pts[ia], pts[ib], pts[ic], px, py)) continue;
+		f4 pl; if (!plane_from_points(p3[ia], p3[ib], p3[ic], &pl)) continue;
+		int cnt = 0; for (int s = 0; s < vc; ++s) if (plane_dist(pl, p3[s]) / dd < thr) ++cnt;
+		if (cnt < 6) continue;
+		if (cnt > max_count) { max_count = cnt; min_cost = plane_dist(pl, c3); best = pl; has = 1; ua = ia; ub = ib; uc = ic; }
+		else if (cnt == max_count) { const float cd = plane_dist(pl, c3); if (cd < min_cost) { min_cost = cd; best = pl; ua = ia; ub = ib; uc = ic; } }
+	}
+	if (!has) { c->reliable[ctr] = 0; return; }
+	float wgt[32];
+	for (int i = 0; i < vc; ++i) {
+		float d = plane_dist(best, p3[i]);
+		if (d / dd >= thr) { pts[i][0] = pts[i][1] = -1; wgt[i] = FLT_MAX; continue; }
+		if (i == ua || i == ub || i == uc) d -= 1.0f;
+		wgt[i] = d;
+	}
+	for (int i = 1; i < vc; ++i) {                                          /* sort_small_weighted, APD.cu:14-27 */
+		const int16_t t0 = pts[i][0], t1 = pts[i][1]; const float tw = wgt[i]; int j = i;
+		for (; j >= 1 && tw < wgt[j - 1]; --j) { pts[j][0] = pts[j - 1][0]; pts[j][1] = pts[j - 1][1]; wgt[j] = wgt[j - 1]; }
+		pts[j][0] = t0; pts[j][1] = t1; wgt[j] = tw;
+	}
+	for (int k = 1; k < NEIGHBOUR_NUM; ++k) { an[2 * k] = pts[k - 1][0]; an[2 * k + 1] = pts[k - 1][1]; }
+	c->reliable[ctr] = 1;
+}
+
+/* RANSACToGetFitPlane, APD.cu:2272-2384 */
+static void fit_plane_pixel(Ctx *c, int px, int py) {
+	const int W = c->W; const size_t ctr = (size_t)py * W + px; const Camera *rc = &c->cams[0];
+	if (c->states[ctr] != WEAK) { c->fit[ctr] = c->planes[ctr]; return; }
+	const int16_t *an = &c->anchors[ctr * NEIGHBOUR_NUM * 2];
+	int16_t pts[8][2]; f3 p3[8]; int cnt = 0;
+	for (int k = 1; k < NEIGHBOUR_NUM; ++k) {
+		const int sx = an[2 * k], sy = an[2 * k + 1];
+		if (sx == -1 || sy == -1) continue;
+		const float depth = depth_from_plane(rc, c->planes[(size_t)sy * W + sx], sx, sy);
+		pts[cnt][0] = (int16_t)sx; pts[cnt][1] = (int16_t)sy; p3[cnt] = point3(rc, sx, sy, depth); ++cnt;
+	}
+	if (cnt < 3) { c->fit[ctr] = c->planes[ctr]; return; }
+	Rng *r = &c->rng[ctr];
+	float min_cost = FLT_MAX; f4 best = {0, 0, 0, 0}; int has = 0;
+	for (int it = 0; it < 50; ++it) {
+		const int ia = (int)(rng_next(r) % (uint32_t)cnt), ib = (int)(rng_next(r) % (uint32_t)cnt), ic = (int)(rng_next(r) % (uint32_t)cnt);
+		if (ia == ib || ib == ic || ia == ic) continue;
+		if (!point_in_triangle(pts[ia], pts[ib], pts[ic], px, py)) continue;
+		f4 pl; if (!plane_from_points(p3[ia], p3[ib], p3[ic], &pl)) continue;
+		float cost = 0.0f;
+		for (int s = 0; s < cnt; ++s) { if (s == ia || s == ib || s == ic) continue; cost += plane_dist(pl, p3[s]); }
+		if (cost < min_cost) { min_cost = cost; best = pl; has = 1; }
+		if (min_cost == 0.0f) break;
+	}
+	if (has) {
+		const float depth = depth_from_plane(rc, c->planes[ctr], px, py);
+		f4 v = view_dir(rc, px, py, depth);
+		if (v.x * best.x + v.y * best.y + v.z * best.z > 0.0f) { best.x = -best.x; best.y = -best.y; best.z = -best.z; best.w = -best.w; }
+		c->fit[ctr] = best;
+	} else { f4 z = {0, 0, 0, 0}; c->fit[ctr] = z; }
+}
+
+/* one window of ComputeBilateralNCCNew: radius 5, step `inc` around (cx, cy), all warped by H (APD.cu:424-520) */
+static float ncc_window(const Ctx *c, int src, const float H[9], int cx, int cy, int inc) {
+	const float *ref = c->images, *img = c->images + (size_t)src * c->W * c->H;
+	float sr = 0, srr = 0, ss = 0, sss = 0, srs = 0, sw = 0;
+	for (int i = -5; i <= 5; i += inc) {
+		float a = 0, aa = 0, b = 0, bb = 0, ab = 0, w = 0;
+		for (int j = -5; j <= 5; j += inc) {
+			float rp = tex2d(ref, c->W, c->H, cx + i + 0.5f, cy + j + 0.5f);
+			float sx, sy; warp(H, (float)(cx + i), (float)(cy + j), &sx, &sy);
+			float sp = tex2d(img, c->W, c->H, sx + 0.5f, sy + 0.5f);
+			a += rp; aa += rp * rp; b += sp; bb += sp * sp; ab += rp * sp; w += 1.0f;
+		}
+		sr += a; srr += aa; ss += b; sss += bb; srs += ab; sw += w;
+	}
+	float inv = 1.0f / sw; sr *= inv; srr *= inv; ss *= inv; sss *= inv; srs *= inv;
+	float vr = srr - sr * sr, vs = sss - ss * ss;
+	if (vr < 1e-5f || vs < 1e-5f) return 2.0f;
+	return fmaxf(0.0f, fminf(2.0f, 1.0f - (srs - sr * ss) / sqrtf(vr * vs)));
+}
+
+/* ComputeBilateralNCCNew, APD.cu:400-528: the pixel's own 6x6 window (weight 0.25) + 3x3 windows on the anchors
+ * (mean, weight 0.75); an anchor that projects outside the source view counts as cost 2 if the anchor selected that view */
+static float ncc_deform(const Ctx *c, int px, int py, int src, f4 pl) {
+	const Camera *rc = &c->cams[0], *sc = &c->cams[src];
+	const int16_t *an = &c->anchors[((size_t)py * c->W + px) * NEIGHBOUR_NUM * 2];
+	float H[9]; homography(rc, sc, pl, H);
+	float cx, cy; warp(H, (float)px, (float)py, &cx, &cy);
+	if (cx >= sc->width || cx < 0.0f || cy >= sc->height || cy < 0.0f) return 2.0f;
+	float center_cost = 0.0f, strong_cost = 0.0f; int cnt = 0;
+	for (int k = 0; k < NEIGHBOUR_NUM; ++k) {
+		const int qx = an[2 * k], qy = an[2 * k + 1];
+		if (qx == -1 || qy == -1) continue;
+		float sx, sy; warp(H, (float)qx, (float)qy, &sx, &sy);
+		if (sx < 0.0f || sy < 0.0f || sx >= (float)c->W || sy >= (float)c->H) {
+			if (k == 0) return 2.0f;
+			if (isset(c->views[(size_t)qy * c->W + qx], src - 1)) { strong_cost += 2.0f; ++cnt; }
+			continue;
+		}
+		if (k == 0) center_cost = ncc_window(c, src, H, qx, qy, 2);
+		else { strong_cost += ncc_window(c, src, H, qx, qy, 5); ++cnt; }
+	}
+	if (cnt == 0) return center_cost;
+	strong_cost /= (float)cnt;
+	if (strong_cost > 2.0f) strong_cost = 2.0f;
+	return (float)(center_cost * 0.25 + strong_cost * 0.75);
+}
+
+static float weak_cost(const Ctx *c, int px, int py, f4 pl, const uint8_t *vw, float wn) {      /* APD.cu:918-927, 1464-1471 */
+	const int S = c->p.num_images - 1; float acc = 0.0f;
+	for (int v = 0; v < S; ++v) {
+		if (vw[v] == 0) continue;
+		float cost = ncc_deform(c, px, py, v + 1, pl);
+		if (c->p.geom_consistency) cost += c->p.geom_factor * geom_cost(c, px, py, v + 1, pl);
+		acc += vw[v] * cost;
+	}
+	return acc / wn;
+}
+
+/* CheckerboardPropagationWeak + PlaneHypothesisRefinementWeak, APD.cu:1323-1508, :892-980 */
+static void weak_pixel(Ctx *c, int px, int py, int iter) {
+	const int W = c->W, S = c->p.num_images - 1; const size_t ctr = (size_t)py * W + px; const Camera *rc = &c->cams[0];
+	const int16_t *an = &c->anchors[ctr * NEIGHBOUR_NUM * 2];
+	float ca[8][32]; memset(ca, 0, sizeof(ca)); ca[0][0] = 2.0f;          /* `= {2.0f}` sets [0][0] only (:1345) */
+	int flag[8] = {0}; size_t pos[8] = {0};
+	for (int k = 0; k < 8; ++k) {                                          /* candidates: planes of the STRONG anchors (:1352-1363) */
+		const int qx = an[2 * (k + 1)], qy = an[2 * (k + 1) + 1];
+		if (qx == -1 || qy == -1) continue;
+		if (c->states[(size_t)qy * W + qx] != STRONG) continue;
+		flag[k] = 1; pos[k] = (size_t)qy * W + qx;
+		for (int v = 0; v < S; ++v) ca[k][v] = ncc_deform(c, px, py, v + 1, c->planes[pos[k]]);
+	}
+	uint8_t *vw = &c->vw[ctr * MAX_IMAGES]; memset(vw, 0, MAX_IMAGES);
+	float prob[32] = {0};
+	float thr = (float)(0.8 * expf((iter * iter) / (-90.0f)));
+	for (int v = 0; v < S; ++v) {                                          /* view selection (:1365-1434) */
+		float prior = 0.0f;
+		for (int k = 1; k < NEIGHBOUR_NUM; ++k) { const int qx = an[2 * k], qy = an[2 * k + 1]; if (qx == -1 || qy == -1) continue;
+			prior += isset(c->views[(size_t)qy * W + qx], v) ? 0.9f : 0.1f; }
+		float count = 0, tmpw = 0; int bad = 0;
+		for (int k = 0; k < 8; ++k) { if (ca[k][v] < thr) { tmpw += expf(ca[k][v] * ca[k][v] / (-0.18f)); count++; } if (ca[k][v] > 1.2f) bad++; }
+		if (count > 2 && bad < 3) prob[v] = tmpw / count; else if (bad < 3) prob[v] = expf(thr * thr / (-0.32f));
+		prob[v] *= prior;
+	}
+	{ float sum = 0; for (int v = 0; v < S; ++v) sum += prob[v]; float inv = 1.0f / sum, cum = 0;
+	  for (int v = 0; v < S; ++v) { cum += prob[v] * inv; prob[v] = cum; } }
+	Rng *r = &c->rng[ctr];
+	for (int s = 0; s < 15; ++s) { float u = rng_uniform(r) - FLT_EPSILON; for (int v = 0; v < S; ++v) if (prob[v] > u) { vw[v]++; break; } }
+	uint32_t sel = 0; float wn = 0; for (int v = 0; v < S; ++v) if (vw[v] > 0) { sel |= 1u << v; wn += vw[v]; }
+	float fc[8];
+	for (int k = 0; k < 8; ++k) {
+		float acc = 0.0f;
+		for (int v = 0; v < S; ++v) { if (vw[v] == 0) continue; float cost = ca[k][v];
+			if (c->p.geom_consistency) cost += c->p.geom_factor * (flag[k] ? geom_cost(c, px, py, v + 1, c->planes[pos[k]]) : 3.0f);
+			acc += vw[v] * cost; }
+		fc[k] = acc / wn;
+	}
+	int mi = 0; { float m = fc[0]; for (int k = 1; k < 8; ++k) if (fc[k] <= m) { m = fc[k]; mi = k; } }
+	f4 pl = c->planes[ctr];
+	float cost_now = weak_cost(c, px, py, pl, vw, wn); const float cost_stored = cost_now;
+	float depth_now = depth_from_plane(rc, pl, px, py);
+	if (flag[mi]) { f4 cand = c->planes[pos[mi]]; float d = depth_from_plane(rc, cand, px, py);
+		if (d >= c->p.depth_min && d <= c->p.depth_max && fc[mi] < cost_now) { depth_now = d; pl = cand; cost_now = fc[mi]; c->views[ctr] = sel; } }
+	{   /* PlaneHypothesisRefinementWeak: only with a fit plane (:892-980) */
+		const f4 fit = c->fit[ctr];
+		if (!(fit.x == 0.0f && fit.y == 0.0f && fit.z == 0.0f)) {
+			const float dmin = c->p.depth_min, dmax = c->p.depth_max;
+			{ float tc = weak_cost(c, px, py, fit, vw, wn); float d = depth_from_plane(rc, fit, px, py);
+			  if (d >= dmin && d <= dmax && tc < cost_now) { depth_now = d; pl = fit; cost_now = tc; } }
+			float drand = rng_uniform(r) * (dmax - dmin) + dmin; f4 nrand = random_normal(rc, px, py, r, depth_now);
+			float lo = (1 - 0.02f) * depth_now, hi = (1 + 0.02f) * depth_now, dpert = rng_uniform(r) * (hi - lo) + lo;
+			f4 npert = perturbed_normal(rc, px, py, pl, r, (float)(0.02f * 3.14159265358979323846));
+			float ds[5] = {drand, depth_now, drand, depth_now, dpert}; f4 ns[5] = {pl, nrand, nrand, npert, pl};
+			for (int i = 0; i < 5; ++i) { f4 t = ns[i]; t.w = dist2origin(rc, px, py, ds[i], t);
+				float tc = weak_cost(c, px, py, t, vw, wn); float d = depth_from_plane(rc, t, px, py);
+				if (d >= dmin && d <= dmax && tc < cost_now) { depth_now = d; pl = t; cost_now = tc; } }
+		}
+	}
+	f4 final_plane = c->planes[ctr];
+	if (c->p.state == REFINE_INIT) { if ((double)cost_now < (double)cost_stored - 0.1) { final_plane = pl; c->planes[ctr] = pl; } }
+	else { final_plane = pl; c->planes[ctr] = pl; }
+	{   /* "update cost with old method" (:1499-1507) */
+		float acc = 0.0f;
+		for (int v = 0; v < S; ++v) if (vw[v] > 0) acc += vw[v] * ncc_old(c, px, py, v + 1, final_plane);
+		c->costs[ctr] = acc / wn;
+	}
+}
+
+/* APD::RunPatchMatch, APD.cu:2386-2495. Returns the number of stages executed; stage numbering as in
+ * include/apd_b200.h. anchors_out [H*W*9*2] int16, nearest_out [H*W*2] int16, reliable_out [H*W], fit_out [H*W*4]
+ * may be NULL. */
+static int run_impl(Ctx *cp, const float *prior_planes, const uint32_t *prior_views, const uint8_t *prior_states, unsigned long long seed, int stage_end);
+int apd_cpu_run_apd(int W, int H, int N, const float *images, const float *depths, const Camera *cams, const Params *params,
+                    const float *prior_planes, const uint32_t *prior_views, const uint8_t *prior_states, unsigned long long seed,
+                    int stage_end, float *planes, float *costs, uint32_t *views, uint8_t *states, uint8_t *view_weights, uint32_t *rng6,
+                    int16_t *anchors_out, int16_t *nearest_out, uint8_t *reliable_out, float *fit_out) {
 	Ctx c; memset(&c, 0, sizeof(c));
 	c.W = W; c.H = H; c.N = N; c.images = images; c.depths = depths; c.cams = cams; c.p = *params; c.p.num_images = N;
 	const size_t n = (size_t)W * H;
 	c.planes = (f4 *)planes; c.costs = costs; c.views = views; c.states = states; c.vw = view_weights; c.rng = (Rng *)rng6;
+	c.anchors = anchors_out ? anchors_out : (int16_t *)malloc(n * NEIGHBOUR_NUM * 2 * sizeof(int16_t));
+	c.nearest = nearest_out ? nearest_out : (int16_t *)malloc(n * 2 * sizeof(int16_t));
+	c.reliable = reliable_out ? reliable_out : (uint8_t *)malloc(n);
+	c.fit = fit_out ? (f4 *)fit_out : (f4 *)malloc(n * sizeof(f4));
+	memset(c.anchors, 0xff, n * NEIGHBOUR_NUM * 2 * sizeof(int16_t)); memset(c.nearest, 0xff, n * 2 * sizeof(int16_t));
+	memset(c.reliable, 0, n); memset(c.fit, 0, n * sizeof(f4));
+	const int rc = run_impl(&c, prior_planes, prior_views, prior_states, seed, stage_end);
+	if (!anchors_out) free(c.anchors);
+	if (!nearest_out) free(c.nearest);
+	if (!reliable_out) free(c.reliable);
+	if (!fit_out) free(c.fit);
+	return rc;
+}
+int apd_cpu_run(int W, int H, int N, const float *images, const float *depths, const Camera *cams, const Params *params,
+                const float *prior_planes, const uint32_t *prior_views, const uint8_t *prior_states, unsigned long long seed,
+                int stage_end, float *planes, float *costs, uint32_t *views, uint8_t *states, uint8_t *view_weights, uint32_t *rng6) {
+	return apd_cpu_run_apd(W, H, N, images, depths, cams, params, prior_planes, prior_views, prior_states, seed, stage_end,
+	                       planes, costs, views, states, view_weights, rng6, NULL, NULL, NULL, NULL);
+}
+static int run_impl(Ctx *cp, const float *prior_planes, const uint32_t *prior_views, const uint8_t *prior_states, unsigned long long seed, int stage_end) {
+	Ctx c = *cp;
+	const int W = c.W, H = c.H; const Camera *cams = c.cams;
+	float *planes = (float *)c.planes; float *costs = c.costs; uint32_t *views = c.views; uint8_t *states = c.states; uint8_t *view_weights = c.vw;
+#if 0
+	c.W = W; c.H = H; c.N = N; c.images = images; c.depths = depths; c.cams = cams; c.p = *params; c.p.num_images = N;
+	const size_t n = (size_t)W * H;
+	c.planes = (f4 *)planes; c.costs = costs; c.views = views; c.states = states; c.vw = view_weights; c.rng = (Rng *)rng6;
+#endif
+	const size_t n = (size_t)W * H;
+	const int apd_on = c.p.use_APD != 0;
 	memset(costs, 0, n * 4); memset(view_weights, 0, n * MAX_IMAGES);
 	for (size_t i = 0; i < n; ++i) states[i] = (c.p.use_APD && prior_states) ? prior_states[i] : STRONG;    /* APD.cpp:513-548 */
 	if (c.p.state != FIRST_INIT) { memcpy(planes, prior_planes, n * 16); memcpy(views, prior_views, n * 4); }
@@ -421,7 +758,19 @@ int apd_cpu_run(int W, int H, int N, const float *images, const float *depths, c
 	int stage = 0;
 #define DONE() do { if (stage == stage_end) return stage + 1; ++stage; } while (0)
 	init_rng(&c, seed); DONE();
-	DONE(); DONE(); DONE();                                   /* K2-K4: WEAK pixels only */
+	if (apd_on) {
+#pragma omp parallel for schedule(dynamic, 4)
+		for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) nearest_strong_pixel(&c, x, y);                    /* K2 */
+	}
+	DONE();
+	if (apd_on) {
+#pragma omp parallel for schedule(dynamic, 4)
+		for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) gen_anchors_pixel(&c, x, y);                       /* K3 */
+	}
+	DONE();
+	if (apd_on)                                                                                                   /* K4 NeigbourUpdate, APD.cu:1971-1987 */
+		for (size_t i = 0; i < n; ++i) if (states[i] == WEAK && c.reliable[i] != 1) states[i] = UNKNOWN;
+	DONE();
 #pragma omp parallel for schedule(dynamic, 4)
 	for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) init_pixel(&c, x, y);
 	DONE();
@@ -432,7 +781,19 @@ int apd_cpu_run(int W, int H, int N, const float *images, const float *depths, c
 				if (((x + y) & 1) == color && y < half_rows && states[(size_t)y * W + x] != WEAK) strong_pixel(&c, x, y, it);
 			DONE();
 		}
-		DONE(); DONE(); DONE();                               /* K8-K10: WEAK pixels only */
+		if (apd_on) {
+#pragma omp parallel for schedule(dynamic, 4)
+			for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) fit_plane_pixel(&c, x, y);                     /* K8 */
+		}
+		DONE();
+		for (int color = 0; color < 2; ++color) {                                                                 /* K9 / K10 */
+			if (apd_on) {
+#pragma omp parallel for schedule(dynamic, 4)
+				for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x)
+					if (((x + y) & 1) == color && y < half_rows && states[(size_t)y * W + x] == WEAK) weak_pixel(&c, x, y, it);
+			}
+			DONE();
+		}
 	}
 	{   /* GetDepthandNormal, APD.cu:1587-1602 */
 		const Camera *rc = &cams[0];
