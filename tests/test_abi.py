@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for hdr in ("apd_b200.h", "apd_scene.h", "apd_io.h"):
+    for hdr in ("apd_b200.h", "apd_scene.h", "apd_io.h", "apd_fusion.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(apd_[a-z_]+)\s*\(", src))
