@@ -1,8 +1,9 @@
 """`python -m apd_mvs_b200.main dense_folder [gpu_index]` - the reference's command line (main.cpp:140-217) on the
 scene layer: reads pair.txt, images/*.jpg, cams/*_cam.txt, runs the 4*round_num passes with everything resident on
-the GPU and writes APD/<id>/{depths.dmb, normals.dmb, weak.bin, selected_views.bin} once at the end (the reference
-rewrites them after every pass and deletes them after fusion; fusion itself, RunFusion APD.cpp:826-977, is not part of
-this path). JPEG decoding uses the Python cv2 module of this image (the C++ OpenCV the reference links is absent)."""
+the GPU, writes APD/<id>/{depths.dmb, normals.dmb, weak.bin, selected_views.bin} once at the end (the reference rewrites
+them after every pass and deletes them after fusion) and fuses the depth maps on the GPU into APD/APD.ply (RunFusion,
+APD.cpp:826-977 -> include/apd_fusion.h). JPEG decoding uses the Python cv2 module of this image (the C++ OpenCV the
+reference links is absent)."""
 from __future__ import annotations
 
 import os
@@ -10,6 +11,7 @@ import sys
 
 import numpy as np
 
+from . import fusion as F
 from . import io as IO
 from . import pipeline as P
 from .scene import CAMERA_DTYPE
@@ -55,6 +57,22 @@ def main(argv=None):
         IO.WriteBinMat(os.path.join(out, "normals.dmb"), scene.Normal(ref))
         IO.WriteBinMat(os.path.join(out, "weak.bin"), scene.States(ref))
         IO.WriteBinMat(os.path.join(out, "selected_views.bin"), scene.SelectedViews(ref))
+    # RunFusion (main.cpp:219): colour images at the depth-map size, optional blocks/mask_<id>.jpg
+    import cv2
+    fu = F.Fusion(len(ids), scene.W, scene.H, device=gpu)
+    block_dir = os.path.join(dense_folder, "blocks")
+    for k, image_id in enumerate(ids):
+        if scene.ResultSize(k) != (scene.W, scene.H):
+            raise RuntimeError("fusion needs full-resolution depth maps for every view (is every image a reference in pair.txt?)")
+        bgr = cv2.imread(os.path.join(dense_folder, "images", IO.ToFormatIndex(image_id) + ".jpg"), cv2.IMREAD_COLOR)
+        block = cv2.imread(os.path.join(block_dir, f"mask_{image_id}.jpg"), cv2.IMREAD_GRAYSCALE) if os.path.isdir(block_dir) else None
+        fu.SetView(k, bgr, cams[k], scene.Depth(k), scene.Normal(k), scene.States(k), block)
+    for ref, srcs in pairs:
+        fu.AddProblem(ref, srcs)
+    xyz, _ = fu.RunFusion()
+    fu.ExportPointCloud(os.path.join(dense_folder, "APD", "APD.ply"))
+    print(f"Fused {len(xyz)} points in {fu.Timing()['gpu_ms']:.1f} ms")
+    fu.close()
     scene.close()
     print("All done")
     return 0

@@ -164,3 +164,6 @@ def test_dense_folder_command_line(tmp_path):
         assert np.array_equal(w, sc.States(k)) and np.array_equal(v.view(np.uint32), sc.SelectedViews(k))
         assert (d > 0).mean() > 0.7
     sc.close()
+    import fusion_tools as FT
+    xyz, bgr = FT.read_ply(tmp_path / "APD" / "APD.ply")           # RunFusion output (main.cpp:219)
+    assert len(xyz) > 0.3 * W * H and np.isfinite(xyz).all()
