@@ -466,17 +466,20 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 
 	// candidates = current planes of the anchors that are (still) STRONG (APD.cu:1352-1363)
 	unsigned flags = 0u; int pos[8];
-#pragma unroll 1
+#pragma unroll
 	for (int k = 0; k < 8; ++k) {
 		const short2 q = an.p[k + 1];
 		pos[k] = 0;
-		const bool ok = !(q.x == -1 || q.y == -1) && a.states[q.x + q.y * W] == APD_STRONG;
-		if (ok) {
-			flags |= 1u << k; pos[k] = q.x + q.y * W;
-			const float4 pl = a.planes[pos[k]];
-			for (int v = 0; v < S; ++v) CM(k, v) = ncc_deform(a, rc, sv[v], v, pl, an, rcol, px, py, inv36, inv9);
-		} else {
-			for (int v = 0; v < S; ++v) CM(k, v) = (k == 0 && v == 0) ? 2.0f : 0.0f;      // `= {2.0f}` quirk, APD.cu:1345
+		if (!(q.x == -1 || q.y == -1) && a.states[q.x + q.y * W] == APD_STRONG) { flags |= 1u << k; pos[k] = q.x + q.y * W; }
+	}
+	// view-major order: the eight candidate planes are neighbouring surfaces, so their footprints in ONE source view
+	// overlap in L1; plane-major order walked through all views between two visits of the same texels
+#pragma unroll 1
+	for (int v = 0; v < S; ++v) {
+#pragma unroll 1
+		for (int k = 0; k < 8; ++k) {
+			if ((flags >> k) & 1u) CM(k, v) = ncc_deform(a, rc, sv[v], v, a.planes[pos[k]], an, rcol, px, py, inv36, inv9);
+			else CM(k, v) = (k == 0 && v == 0) ? 2.0f : 0.0f;                            // `= {2.0f}` quirk, APD.cu:1345
 		}
 	}
 	// view selection (APD.cu:1365-1434): priors from every existing anchor, STRONG or not
