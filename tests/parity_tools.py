@@ -91,3 +91,26 @@ def depth_stats(mine_planes, ref_planes, depth_min, depth_max):
     rel = np.abs(dm - dr) / np.maximum(np.abs(dr), 1e-12)
     return {"depth_L1_norm": float(np.abs(dm - dr)[ok].mean() / (depth_max - depth_min)),
             "frac_rel_le_1e-4": float((rel[ok] <= 1e-4).mean()), "valid": float(ok.mean())}
+
+
+def random_config(rng):
+    """One random configuration of the sweep used by tools/parity_fuzz.py and tests/test_parity_gpu.py."""
+    W, H = int(rng.integers(40, 260)), int(rng.integers(40, 200))
+    S = int(rng.choice([1, 2, 3, 4, 5, 7, 9, 12, 17, 31]))
+    state = int(rng.choice([E.FIRST_INIT, E.REFINE_INIT, E.REFINE_ITER]))
+    use_apd = bool(rng.integers(0, 2)) and state != E.FIRST_INIT
+    geom = bool(rng.integers(0, 2)) and state == E.REFINE_ITER
+    kw = dict(state=state, use_apd=use_apd, geom=geom, iters=int(rng.integers(1, 4)), rotate_time=int(rng.choice([1, 2, 4])),
+              top_k=int(rng.choice([1, 2, 4, 5])), weak_peak_radius=int(rng.choice([2, 4, 6])),
+              ransac_threshold=float(rng.choice([0.005, 0.00625, 0.00875])), seed=int(rng.integers(1, 1 << 30)))
+    if S > 12:
+        W, H = min(W, 120), min(H, 90)
+    return W, H, S, kw, int(rng.integers(1, 1 << 40))
+
+
+def final_diff(case, curand_seed):
+    """Bit-difference fractions of the final outputs, product vs reference oracle."""
+    ref = make_reference(case, seed=curand_seed); ref.run(); rp, rs, rv = ref.outputs(); ref.close()
+    apd = make_product(case, seed=curand_seed); apd.RunPatchMatch(); mine = product_state(apd); apd.close()
+    return diff_state({"planes": mine["planes"], "states": mine["states"], "views": mine["views"]},
+                      {"planes": rp, "states": rs, "views": rv}, fields=("planes", "states", "views"))

@@ -156,3 +156,15 @@ def test_error_behaviour_matches_reference_preconditions():
     with pytest.raises(E.ApdError):           # priors missing (APD.cpp:552-581)
         apd2.RunPatchMatch()
     apd2.close()
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libapd_ref.so not built")
+def test_random_configurations_bit_exact():
+    """A slice of the randomised sweep of tools/parity_fuzz.py (sizes, 1..31 source views, run states, APD, geometric term,
+    iterations, rotate_time, top_k, seeds)."""
+    rng = np.random.default_rng(31337)
+    for i in range(24):
+        W, H, S, kw, curand_seed = T.random_config(rng)
+        case = T.build_case(W, H, S, device="cuda", **kw)
+        d = T.final_diff(case, curand_seed)
+        assert all(v == 0.0 for v in d.values()), (i, W, H, S, kw, d)

@@ -16,22 +16,10 @@ n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2024)
 rows, bad = [], 0
 for i in range(n_cases):
-    W, H = int(rng.integers(40, 260)), int(rng.integers(40, 200))
-    S = int(rng.choice([1, 2, 3, 4, 5, 7, 9, 12, 17, 31]))
-    state = int(rng.choice([E.FIRST_INIT, E.REFINE_INIT, E.REFINE_ITER]))
-    use_apd = bool(rng.integers(0, 2)) and state != E.FIRST_INIT
-    geom = bool(rng.integers(0, 2)) and state == E.REFINE_ITER
-    kw = dict(state=state, use_apd=use_apd, geom=geom, iters=int(rng.integers(1, 4)), rotate_time=int(rng.choice([1, 2, 4])),
-              top_k=int(rng.choice([1, 2, 4, 5])), weak_peak_radius=int(rng.choice([2, 4, 6])),
-              ransac_threshold=float(rng.choice([0.005, 0.00625, 0.00875])), seed=int(rng.integers(1, 1 << 30)))
-    if S > 12:
-        W, H = min(W, 120), min(H, 90)
+    W, H, S, kw, curand_seed = T.random_config(rng)
+    state, use_apd, geom = kw["state"], kw["use_apd"], kw["geom"]
     case = T.build_case(W, H, S, device="cuda", **kw)
-    curand_seed = int(rng.integers(1, 1 << 40))
-    ref = T.make_reference(case, seed=curand_seed); ref.run(); rp, rs, rv = ref.outputs(); ref.close()
-    apd = T.make_product(case, seed=curand_seed); apd.RunPatchMatch(); mine = T.product_state(apd); apd.close()
-    d = T.diff_state({"planes": mine["planes"], "states": mine["states"], "views": mine["views"]},
-                     {"planes": rp, "states": rs, "views": rv}, fields=("planes", "states", "views"))
+    d = T.final_diff(case, curand_seed)
     ok = all(v == 0.0 for v in d.values())
     bad += 0 if ok else 1
     rows.append({"W": W, "H": H, "S": S, **{k: v for k, v in kw.items()}, "curand_seed": curand_seed, "diff": d, "ok": ok})
