@@ -167,3 +167,38 @@ def test_dense_folder_command_line(tmp_path):
     import fusion_tools as FT
     xyz, bgr = FT.read_ply(tmp_path / "APD" / "APD.ply")           # RunFusion output (main.cpp:219)
     assert len(xyz) > 0.15 * W * H and np.isfinite(xyz).all()
+
+
+def test_schedule_and_fusion_against_committed_golden():
+    """tests/golden/pipeline_1010x64_v3.json (made from the reference by tests/golden/make_golden_pipeline.py): the whole
+    2-round schedule and the fusion of its maps, compared by SHA-256 - needs no oracle library at run time."""
+    import hashlib
+    import json
+    import os
+    import fusion_tools as FT
+    from apd_mvs_b200 import fusion as F
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pipeline_1010x64_v3.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    from apd_mvs_b200.scene import CAMERA_DTYPE
+    inp = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pipeline_1010x64_v3_inputs.npz"))
+    images = inp["images"].astype(np.float32)
+    cams = np.frombuffer(inp["cameras"].tobytes(), dtype=CAMERA_DTYPE).copy()
+    assert sha(images) == g["images_sha"]
+    pairs = P.ring_pairs(g["views"], g["src"])
+    sc = P.Scene(images, cams, pairs, seed=g["seed"])
+    sc.Run()
+    for v, r in enumerate(g["results"]):
+        assert sha(sc.Depth(v)) == r["depth"], (v, "depth")
+        assert sha(sc.Normal(v)) == r["normal"], (v, "normal")
+        assert sha(sc.States(v)) == r["states"] and sha(sc.SelectedViews(v)) == r["views"], v
+        assert np.allclose(sc.Depth(v)[::16, ::101].ravel()[:12], r["depth_samples"], rtol=0, atol=0)
+    fu = F.Fusion(g["views"], g["W"], g["H"])
+    bgr = FT.colour_images(images)
+    for v in range(g["views"]):
+        fu.SetView(v, bgr[v], cams[v], sc.Depth(v), sc.Normal(v), sc.States(v))
+    for r, s in pairs:
+        fu.AddProblem(r, s)
+    xyz, col = fu.RunFusion()
+    assert len(xyz) == g["fusion"]["points"]
+    assert sha(xyz) == g["fusion"]["xyz"] and sha(col.astype(np.uint8)) == g["fusion"]["bgr"]
+    fu.close(); sc.close()
