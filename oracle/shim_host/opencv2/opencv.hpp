@@ -112,7 +112,7 @@ public:
 };
 
 // Raw container: "APDRAW\0\0", int32 rows, cols, channels, then rows*cols*channels bytes (BGR order for 3 channels).
-inline Mat imread(const std::string &path, int flags) {
+inline Mat imread(const std::string &path, int flags = IMREAD_COLOR) {
 	Mat m;
 	FILE *f = fopen(path.c_str(), "rb");
 	if (!f) return m;
@@ -120,6 +120,13 @@ inline Mat imread(const std::string &path, int flags) {
 	if (fread(magic, 1, 8, f) == 8 && memcmp(magic, "APDRAW\0\0", 8) == 0 && fread(hdr, 4, 3, f) == 3) {
 		const int want = (flags == IMREAD_GRAYSCALE) ? 1 : 3;
 		if (hdr[2] == want) { m.create(hdr[0], hdr[1], want == 1 ? CV_8UC1 : CV_8UC3); if (fread(m.data, 1, (size_t)hdr[0] * m.step, f) != (size_t)hdr[0] * m.step) m = Mat(); }
+		else if (hdr[2] == 3 && want == 1) {      // BGR -> grey with OpenCV's fixed-point weights (B 1868, G 9617, R 4899, >> 14)
+			std::vector<uchar> bgr((size_t)hdr[0] * hdr[1] * 3);
+			if (fread(bgr.data(), 1, bgr.size(), f) == bgr.size()) {
+				m.create(hdr[0], hdr[1], CV_8UC1);
+				for (size_t i = 0; i < (size_t)hdr[0] * hdr[1]; ++i) m.data[i] = (uchar)((bgr[3 * i] * 1868 + bgr[3 * i + 1] * 9617 + bgr[3 * i + 2] * 4899 + 8192) >> 14);
+			}
+		}
 	}
 	fclose(f);
 	return m;
