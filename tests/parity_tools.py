@@ -94,7 +94,7 @@ def depth_stats(mine_planes, ref_planes, depth_min, depth_max):
 
 
 def random_config(rng):
-    """One random configuration of the sweep used by tools/parity_fuzz.py and tests/test_parity_gpu.py."""
+    """One random configuration of the sweep used by tests/tools/parity_fuzz.py and tests/test_parity_gpu.py."""
     W, H = int(rng.integers(40, 260)), int(rng.integers(40, 200))
     S = int(rng.choice([1, 2, 3, 4, 5, 7, 9, 12, 17, 31]))
     state = int(rng.choice([E.FIRST_INIT, E.REFINE_INIT, E.REFINE_ITER]))

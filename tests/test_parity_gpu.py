@@ -160,7 +160,7 @@ def test_error_behaviour_matches_reference_preconditions():
 
 @pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libapd_ref.so not built")
 def test_random_configurations_bit_exact():
-    """A slice of the randomised sweep of tools/parity_fuzz.py (sizes, 1..31 source views, run states, APD, geometric term,
+    """A slice of the randomised sweep of tests/tools/parity_fuzz.py (sizes, 1..31 source views, run states, APD, geometric term,
     iterations, rotate_time, top_k, seeds)."""
     rng = np.random.default_rng(31337)
     for i in range(24):

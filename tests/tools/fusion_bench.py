@@ -2,7 +2,7 @@
 """Fusion on the GPU (include/apd_fusion.h) against the reference's unmodified RunFusion on the host CPU
 (oracle/_ref/libapd_fusion_ref.so), on the depth maps of a real run of the pass schedule.
 
-    python tools/fusion_bench.py --width 1920 --height 1080 --views 8 --src 5 [--out profiles/...json]"""
+    python tests/tools/fusion_bench.py --width 1920 --height 1080 --views 8 --src 5 [--out profiles/...json]"""
 import argparse
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 

@@ -2,7 +2,7 @@
 """Wall time of the reference's own program (oracle/_ref/apd_main_ref) and of the same main.cpp linked against the facade +
 libapd_b200.so (oracle/_ref/apd_main_b200) on one synthetic dense_folder; checks that APD.ply is byte-identical.
 
-    python tools/main_program_bench.py --width 1000 --height 750 --views 6 --src 4 [--out profiles/...json]"""
+    python tests/tools/main_program_bench.py --width 1000 --height 750 --views 6 --src 4 [--out profiles/...json]"""
 import argparse
 import json
 import os
@@ -11,7 +11,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 

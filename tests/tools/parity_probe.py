@@ -1,8 +1,9 @@
 """GPU diagnostic (run under gpurun): stage-by-stage bit diff of the product against the reference
 oracle, then per-stage timings of both on a larger case. Writes gpurun_out/parity_probe.json."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import parity_tools as T
 from apd_mvs_b200 import engine as E

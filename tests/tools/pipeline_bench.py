@@ -2,7 +2,7 @@
 """Whole-schedule timing of the scene layer (include/apd_scene.h) against the reference's per-(problem, pass)
 object lifetime, on the same box and the same synthetic multi-view scene (SURVEY §8d cfg 4, scaled by --views).
 
-    python tools/pipeline_bench.py --width 1920 --height 1080 --views 8 --src 5 [--no-reference]
+    python tests/tools/pipeline_bench.py --width 1920 --height 1080 --views 8 --src 5 [--no-reference]
 
 ours      : Scene.Run() = 4*round_num passes over all problems, everything resident in HBM.
 reference : for every (problem, pass) construct + upload + APD::RunPatchMatch + download + destroy of the UNMODIFIED
@@ -15,7 +15,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 

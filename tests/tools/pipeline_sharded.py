@@ -3,7 +3,7 @@
 broadcast of images + cameras at setup, per-pass NCCL broadcasts of the depth maps (cfg 4 shape).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \\
-        tools/pipeline_sharded.py --width 1920 --height 1080 --views 8 --src 5 [--check]
+        tests/tools/pipeline_sharded.py --width 1920 --height 1080 --views 8 --src 5 [--check]
 
 --check: rank 0 also runs the reference driver emulation with the same visibility rule
 (oracle.ref_pipeline.RefPipeline.run_pass(world=N)) and every rank compares the views it owns bit for bit."""
@@ -13,7 +13,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
