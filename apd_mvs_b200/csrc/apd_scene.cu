@@ -443,6 +443,30 @@ extern "C" int apd_scene_get_normal(apd_scene_handle s, int view, float *normal_
 	return APD_OK;
 }
 
+__global__ void k_pack_planes(const float *__restrict__ normal, const float *__restrict__ depth, float4 *__restrict__ planes, size_t n) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) planes[i] = make_float4(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2], depth[i]);
+}
+
+extern "C" int apd_scene_set_result(apd_scene_handle s, int view, int width, int height, const float *depth, const float *normal_xyz,
+                                    const uint8_t *states, const uint32_t *selected_views) {
+	if (!s || view < 0 || view >= s->n_views || !depth || !normal_xyz || !states || !selected_views) return APD_E_ARG;
+	if (width < 1 || height < 1 || (size_t)width * height > (size_t)s->W * s->H) return sfail(s, APD_E_ARG, "result larger than the full-resolution buffers");
+	CKS(cudaSetDevice(s->device));
+	const size_t n = (size_t)width * height;
+	ViewResult &r = s->res[view];
+	// the normals travel through tmp_planes (3 floats per pixel fit into its 4)
+	CKS(cudaMemcpyAsync(r.depth, depth, n * 4, cudaMemcpyDefault, s->stream));
+	CKS(cudaMemcpyAsync(s->tmp_planes, normal_xyz, n * 12, cudaMemcpyDefault, s->stream));
+	k_pack_planes<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const float *>(s->tmp_planes), r.depth, r.planes, n);
+	CKS(cudaMemcpyAsync(r.states, states, n, cudaMemcpyDefault, s->stream));
+	CKS(cudaMemcpyAsync(r.views, selected_views, n * 4, cudaMemcpyDefault, s->stream));
+	CKS(cudaGetLastError());
+	CKS(cudaStreamSynchronize(s->stream));
+	r.W = width; r.H = height;
+	return APD_OK;
+}
+
 extern "C" int apd_scene_result_device(apd_scene_handle s, int view, void **planes, void **depth, void **states, void **views) {
 	if (!s || view < 0 || view >= s->n_views) return APD_E_ARG;
 	const ViewResult &r = s->res[view];

@@ -29,6 +29,7 @@ def _bind(lib):
     lib.apd_scene_result_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
     for name in ("depth", "normal", "states", "views"):
         getattr(lib, "apd_scene_get_" + name).argtypes = [vp, ci, vp]
+    lib.apd_scene_set_result.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp]
     lib.apd_scene_result_device.argtypes = [vp, ci, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.apd_scene_mark_result.argtypes = [vp, ci, ci, ci]
     lib.apd_scene_get_scaled_image.argtypes = [vp, ci, ci, vp]
@@ -104,6 +105,14 @@ class Scene:
     def Normal(self, view): return self._get("normal", view, (3,), np.float32)
     def States(self, view): return self._get("states", view, (), np.uint8)
     def SelectedViews(self, view): return self._get("views", view, (), np.uint32)
+
+    def SetResult(self, view: int, depth, normal, states, selected_views):
+        """Checkpoint / resume: load a view's maps (as returned by Depth / Normal / States / SelectedViews or read from
+        its depths.dmb / normals.dmb / weak.bin / selected_views.bin)."""
+        d = np.ascontiguousarray(depth, np.float32); n = np.ascontiguousarray(normal, np.float32)
+        st = np.ascontiguousarray(states, np.uint8); sv = np.ascontiguousarray(selected_views).view(np.uint32)
+        h, w = d.shape
+        self._ck(self.L.apd_scene_set_result(self._h, view, w, h, d.ctypes.data, n.ctypes.data, st.ctypes.data, sv.ctypes.data))
 
     # ---- multi-GPU hand-over (used by ShardedScene)
     def depth_tensor(self, view: int, width: int, height: int):

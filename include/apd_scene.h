@@ -70,6 +70,11 @@ int apd_scene_get_depth(apd_scene_handle s, int view, float *depth);
 int apd_scene_get_normal(apd_scene_handle s, int view, float *normal_xyz);
 int apd_scene_get_states(apd_scene_handle s, int view, uint8_t *states);
 int apd_scene_get_views(apd_scene_handle s, int view, uint32_t *selected_views);
+/* Checkpoint / resume: load a view's four maps as they were read back (or read from its .dmb / .bin files), so that a new
+ * scene continues the schedule where a previous process stopped - the role the result files play between the reference's
+ * passes (APD.cpp:492-581). Pointers may be host or device memory. */
+int apd_scene_set_result(apd_scene_handle s, int view, int width, int height, const float *depth, const float *normal_xyz,
+                         const uint8_t *states, const uint32_t *selected_views);
 /* Multi-GPU hand-over: device pointers of a view's result buffers (each sized for the full
  * resolution; planes = float4 per pixel: normal xyz + depth w) so that a collective can write a peer's result in
  * place, and the declaration that they now hold a width x height result. Ranks shard the problems; between passes

@@ -202,3 +202,31 @@ def test_schedule_and_fusion_against_committed_golden():
     assert len(xyz) == g["fusion"]["points"]
     assert sha(xyz) == g["fusion"]["xyz"] and sha(col.astype(np.uint8)) == g["fusion"]["bgr"]
     fu.close(); sc.close()
+
+
+def test_checkpoint_and_resume(tmp_path):
+    """Stop after round 0, write the four files of every view, start a NEW scene from them and finish: identical to the
+    uninterrupted schedule (the files are the reference's hand-over between passes)."""
+    from apd_mvs_b200 import io as IO
+    images, cams = make_views(1040, 300, 3)
+    pairs = P.ring_pairs(3, 2)
+    whole = P.Scene(images, cams, pairs, seed=21)
+    whole.Run()
+    first = P.Scene(images, cams, pairs, seed=21)
+    for ps in range(4):
+        first.RunPass(0, ps)
+    for v in range(3):
+        IO.WriteBinMat(tmp_path / f"d{v}.dmb", first.Depth(v)); IO.WriteBinMat(tmp_path / f"n{v}.dmb", first.Normal(v))
+        IO.WriteBinMat(tmp_path / f"w{v}.bin", first.States(v)); IO.WriteBinMat(tmp_path / f"s{v}.bin", first.SelectedViews(v))
+    first.close()
+    second = P.Scene(images, cams, pairs, seed=21)
+    for v in range(3):
+        second.SetResult(v, IO.ReadBinMat(tmp_path / f"d{v}.dmb"), IO.ReadBinMat(tmp_path / f"n{v}.dmb"),
+                         IO.ReadBinMat(tmp_path / f"w{v}.bin"), IO.ReadBinMat(tmp_path / f"s{v}.bin"))
+    for ps in range(4):
+        second.RunPass(1, ps)
+    for v in range(3):
+        assert np.array_equal(bits(second.Depth(v)), bits(whole.Depth(v)))
+        assert np.array_equal(bits(second.Normal(v)), bits(whole.Normal(v)))
+        assert np.array_equal(second.States(v), whole.States(v)) and np.array_equal(second.SelectedViews(v), whole.SelectedViews(v))
+    whole.close(); second.close()
