@@ -452,70 +452,62 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 	// are at different views at the same time, which the layered texture (per-lane layer) permits. The warp
 	// iterates max-over-lanes(#sampled views) times instead of S times.
 	const uint32_t wmask = alive ? temp_sel : 0u;
-	float cost_now;
-	{
-		float acc = 0.0f;
-		uint32_t m = wmask;
-#pragma unroll 1
-		while (__any_sync(0xffffffffu, m != 0u)) {
-			const bool want = m != 0u;
-			const int v = want ? (__ffs(m) - 1) : 0;
-			m &= m - 1u;
-			const float c = NCC(v, pl_now, want);
-			if (want) acc = fmaf((float)vw_get(vw, v), c, acc);
-		}
-		cost_now = acc * inv_wn;
-	}
-	const float cost_stored = cost_now;                   // costs[center] = cost_now (APD.cu:1295)
+	float cost_now = 0.0f, cost_stored = 0.0f;            // costs[center] = cost_now (APD.cu:1295)
 	float depth_now = 1.0f;
 	uint32_t sel_out = 0u; bool sel_write = false;
-	float depth_rand = 1.0f, depth_pert = 1.0f;
-	float4 n_rand = pl_now, n_pert = pl_now;
-	if (alive) {
-		depth_now = plane_depth(rc, pl_now, xf, yf);
-		if ((flags >> best_k) & 1u) {
-			int bp = pos[0];
-#pragma unroll
-			for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
-			const float4 cand = a.planes[bp];
-			const float d = plane_depth(rc, cand, xf, yf);
-			if (d >= a.depth_min && d <= a.depth_max && best_cost < cost_now) {
-				depth_now = d; pl_now = cand; cost_now = best_cost; sel_out = temp_sel; sel_write = true;
-			}
-		}
-		// PlaneHypothesisRefinementStrong, APD.cu:837-890
-		depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
-		n_rand = random_normal(rc, xf, yf, rng, depth_now);
-		const float lo = depth_now * (1.0f - 0.02f);
-		const float span = fmaf(depth_now, 1.0f + 0.02f, -lo);
-		depth_pert = fmaf(span, rng_uniform(rng), lo);     // the do/while never repeats (:860-862)
-		n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
-	}
-	{
-		const float4 n0 = pl_now; const float d0 = depth_now;
+	float depth_rand = 1.0f, depth_pert = 1.0f, d0 = 1.0f;
+	float4 n_rand = pl_now, n_pert = pl_now, n0 = pl_now;
+	// i = -1: the current plane; i = 0..4: PlaneHypothesisRefinementStrong's five hypotheses (APD.cu:837-890). One loop,
+	// one inlined NCC body (the instruction cache is a measured limiter of this kernel).
 #pragma unroll 1
-		for (int i = 0; i < 5; ++i) {
+	for (int i = -1; i < 5; ++i) {
+		float4 t = pl_now; float d = depth_now; bool in_range = true;
+		if (i >= 0) {
 			const float di = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : d0);
-			float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
+			t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
 			t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
 			// A hypothesis is adopted only if its depth is in range and its weighted cost is below cost_now. Costs and
 			// weights are non-negative and every partial sum is rounded monotonically, so (a) an out-of-range
 			// hypothesis and (b) one whose partial sum already reaches cost_now can never be adopted: their remaining
 			// views are not evaluated (the reference evaluates and then discards them).
-			const float d = plane_depth(rc, t, xf, yf);
-			const bool in_range = d >= a.depth_min && d <= a.depth_max;
-			float acc = 0.0f;
-			uint32_t m = in_range ? wmask : 0u;
+			d = plane_depth(rc, t, xf, yf);
+			in_range = d >= a.depth_min && d <= a.depth_max;
+		}
+		float acc = 0.0f;
+		uint32_t m = in_range ? wmask : 0u;
 #pragma unroll 1
-			while (__any_sync(0xffffffffu, m != 0u)) {
-				const bool want = m != 0u;
-				const int v = want ? (__ffs(m) - 1) : 0;
-				m &= m - 1u;
-				const float c = NCC(v, t, want);
-				if (want) { acc = fmaf((float)vw_get(vw, v), c, acc); if (acc * inv_wn >= cost_now) m = 0u; }
-			}
-			const float tc = acc * inv_wn;
+		while (__any_sync(0xffffffffu, m != 0u)) {
+			const bool want = m != 0u;
+			const int v = want ? (__ffs(m) - 1) : 0;
+			m &= m - 1u;
+			const float c = NCC(v, t, want);
+			if (want) { acc = fmaf((float)vw_get(vw, v), c, acc); if (i >= 0 && acc * inv_wn >= cost_now) m = 0u; }
+		}
+		const float tc = acc * inv_wn;
+		if (i >= 0) {
 			if (in_range && tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+		} else {
+			cost_now = tc; cost_stored = tc;
+			if (alive) {
+				depth_now = plane_depth(rc, pl_now, xf, yf);
+				if ((flags >> best_k) & 1u) {
+					int bp = pos[0];
+#pragma unroll
+					for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
+					const float4 cand = a.planes[bp];
+					const float dc = plane_depth(rc, cand, xf, yf);
+					if (dc >= a.depth_min && dc <= a.depth_max && best_cost < cost_now) {
+						depth_now = dc; pl_now = cand; cost_now = best_cost; sel_out = temp_sel; sel_write = true;
+					}
+				}
+				depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
+				n_rand = random_normal(rc, xf, yf, rng, depth_now);
+				const float lo = depth_now * (1.0f - 0.02f);
+				const float span = fmaf(depth_now, 1.0f + 0.02f, -lo);
+				depth_pert = fmaf(span, rng_uniform(rng), lo);     // the do/while never repeats (:860-862)
+				n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
+			}
+			n0 = pl_now; d0 = depth_now;
 		}
 	}
 	slab_exit(a, s_slot, NT);
