@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 		if (fl) pl = a.planes[pos[k]];
 #pragma unroll 1
 		for (int v = 0; v < S; ++v) {
-			const float c = NCC(v, pl, fl);
+			const float c = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], pl), sv[v], fl, tile, C::PW, lx, ly, px, py, inv36);
 			CM(k, v) = fl ? c : ((k == 0 && v == 0) ? 2.0f : 0.0f);
 		}
 	}
