@@ -303,67 +303,73 @@ __device__ __forceinline__ void set_ref_sums(QuadCtx &q, const float *tile, int 
 	q.ref_r = r; q.ref_rr = rr;
 }
 
-template <int SPT = 4, bool ROLL = true>
-__device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc, bool want,
-                                           const float *tile, int pitch, int lx, int ly, int px, int py, float inv_w) {
+// The evaluation in three pieces, so that a caller with a queue of evaluations can keep the fetches of the NEXT one in
+// flight while it accumulates the current one (ncc6_quad below is the plain sequence issue, store, accumulate).
+struct NccFetch { float v[4][9]; unsigned my_quad; bool active; };
+
+// Piece 1: decide who is live, broadcast each owner's homography to its quad, issue all 36 fetches of this lane.
+__device__ __forceinline__ void ncc6_issue(const QuadCtx &q, cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc, bool want,
+                                           int px, int py, NccFetch &f) {
 	// must be called by all 32 lanes of the warp convergently
 	const float pxf = (float)px, pyf = (float)py;
-	const bool active = want && centre_inside(Hm, vc, pxf, pyf);
-	const unsigned ballot = __ballot_sync(0xffffffffu, active);
-	const unsigned my_quad = (ballot >> (q.lane & ~3)) & 0xFu;      // which of my quad's four evaluation slots are live
-	// SPT evaluation slots per trip: 9*SPT fetches are in flight before any result is consumed.
-#pragma unroll 1
-	for (int e0 = 0; e0 < 4; e0 += SPT) {
-		float v[SPT][9];
+	f.active = want && centre_inside(Hm, vc, pxf, pyf);
+	const unsigned ballot = __ballot_sync(0xffffffffu, f.active);
+	f.my_quad = (ballot >> (q.lane & ~3)) & 0xFu;                 // which of my quad's four evaluation slots are live
 #pragma unroll
-		for (int u = 0; u < SPT; ++u) {
-			const int e = e0 + u;
-			if ((ballot & (0x11111111u << e)) == 0u) continue;            // warp-uniform: nobody owns a live slot e
-			float h[9];
+	for (int e = 0; e < 4; ++e) {
+		if ((ballot & (0x11111111u << e)) == 0u) continue;            // warp-uniform: nobody owns a live slot e
+		float h[9];
 #pragma unroll
-			for (int i = 0; i < 9; ++i) h[i] = __shfl_sync(0xffffffffu, Hm.h[i], e, 4);
-			// tap coordinates are small integers: float sums of them are exact, no conversions per tap
-			const float pxe = __shfl_sync(0xffffffffu, pxf, e, 4), pye = __shfl_sync(0xffffffffu, pyf, e, 4);
-			const int lay = __shfl_sync(0xffffffffu, layer, e, 4);
-			if ((my_quad >> e) & 1u) {
-				const float x0 = pxe + ((q.qx != ((e & 1) != 0)) ? -3.f : -5.f), y0 = pye + ((q.qy != ((e & 2) != 0)) ? -3.f : -5.f);
-				// x and y of the projective warp advance as one packed pair (same operations as src_tap)
-				const f32x2 H03 = pk2(h[0], h[3]), H14 = pk2(h[1], h[4]), H25 = pk2(h[2], h[5]);
-				float yf[3]; f32x2 YF[3];
+		for (int i = 0; i < 9; ++i) h[i] = __shfl_sync(0xffffffffu, Hm.h[i], e, 4);
+		// tap coordinates are small integers: float sums of them are exact, no conversions per tap
+		const float pxe = __shfl_sync(0xffffffffu, pxf, e, 4), pye = __shfl_sync(0xffffffffu, pyf, e, 4);
+		const int lay = __shfl_sync(0xffffffffu, layer, e, 4);
+		if ((f.my_quad >> e) & 1u) {
+			const float x0 = pxe + ((q.qx != ((e & 1) != 0)) ? -3.f : -5.f), y0 = pye + ((q.qy != ((e & 2) != 0)) ? -3.f : -5.f);
+			// x and y of the projective warp advance as one packed pair (same operations as src_tap)
+			const f32x2 H03 = pk2(h[0], h[3]), H14 = pk2(h[1], h[4]), H25 = pk2(h[2], h[5]);
+			float yf[3]; f32x2 YF[3];
 #pragma unroll
-				for (int d = 0; d < 3; ++d) { yf[d] = y0 + (float)(4 * d); YF[d] = pk2(yf[d], yf[d]); }
+			for (int d = 0; d < 3; ++d) { yf[d] = y0 + (float)(4 * d); YF[d] = pk2(yf[d], yf[d]); }
 #pragma unroll
-				for (int c = 0; c < 3; ++c) {
-					const float xf = x0 + (float)(4 * c);
-					const f32x2 AXY = mul2(H03, pk2(xf, xf));
-					const float az = h[6] * xf;
+			for (int c = 0; c < 3; ++c) {
+				const float xf = x0 + (float)(4 * c);
+				const f32x2 AXY = mul2(H03, pk2(xf, xf));
+				const float az = h[6] * xf;
 #pragma unroll
-					for (int d = 0; d < 3; ++d) {
-						const f32x2 XY = add2(H25, fma2(H14, YF[d], AXY));
-						const float rz = rcpf(h[8] + fmaf(h[7], yf[d], az));
-						// scalar here: the texture instruction wants (layer, x, y) in consecutive registers, which a
-						// packed result (even/odd pair) can only reach through extra moves
-						float xs, ys; unpk2(XY, xs, ys);
-						v[u][c * 3 + d] = tex2DLayered<float>(tex, fmaf(xs, rz, 0.5f), fmaf(ys, rz, 0.5f), lay);
-					}
+				for (int d = 0; d < 3; ++d) {
+					const f32x2 XY = add2(H25, fma2(H14, YF[d], AXY));
+					const float rz = rcpf(h[8] + fmaf(h[7], yf[d], az));
+					// scalar here: the texture instruction wants (layer, x, y) in consecutive registers, which a
+					// packed result (even/odd pair) can only reach through extra moves
+					float xs, ys; unpk2(XY, xs, ys);
+					f.v[e][c * 3 + d] = tex2DLayered<float>(tex, fmaf(xs, rz, 0.5f), fmaf(ys, rz, 0.5f), lay);
 				}
 			}
 		}
-		// stage the warped patches: tap (2c+qa, 2d+qb) -> T = 12c + 2d + 6qa + qb, slot T*32 + lane
+	}
+}
+
+// Piece 2: stage the warped patches: tap (2c+qa, 2d+qb) -> T = 12c + 2d + 6qa + qb, slot T*32 + lane. The caller
+// synchronises the warp afterwards.
+__device__ __forceinline__ void ncc6_store(const QuadCtx &q, const NccFetch &f) {
 #pragma unroll
-		for (int u = 0; u < SPT; ++u) {
-			const int e = e0 + u;
-			if ((my_quad >> e) & 1u) {
-				const int qd = q.ql ^ e;
-				float *dst = q.slab + (6 * (qd & 1) + (qd >> 1)) * 32 + q.lane;
+	for (int e = 0; e < 4; ++e) {
+		if ((f.my_quad >> e) & 1u) {
+			const int qd = q.ql ^ e;
+			float *dst = q.slab + (6 * (qd & 1) + (qd >> 1)) * 32 + q.lane;
 #pragma unroll
-				for (int c = 0; c < 3; ++c)
+			for (int c = 0; c < 3; ++c)
 #pragma unroll
-					for (int d = 0; d < 3; ++d) dst[(12 * c + 2 * d) * 32] = v[u][c * 3 + d];
-			}
+				for (int d = 0; d < 3; ++d) dst[(12 * c + 2 * d) * 32] = f.v[e][c * 3 + d];
 		}
 	}
-	__syncwarp();
+}
+
+// Piece 3: the owner accumulates its own evaluation from the slab in the reference's order. The caller synchronises
+// the warp before the slab is written again.
+template <bool ROLL>
+__device__ __forceinline__ float ncc6_accum(const QuadCtx &q, bool active, const float *tile, int pitch, int lx, int ly, float inv_w) {
 	float cost = kCostMax;
 	if (active) {
 		NccSums t = {q.ref_r, q.ref_rr, 0.f, 0.f, 0.f};
@@ -372,7 +378,7 @@ __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t
 		// ROLL keeps the accumulation loop small for the instruction cache (two x-offsets per trip)
 #pragma unroll(ROLL ? 1 : 3)
 		for (int i2 = 0; i2 < 3; ++i2) {
-			// the two x-offsets of a trip are independent row sums: their five running sums advance in lock
+			// the two x-offsets of a trip are independent row sums: their running sums advance in lock
 			// step as packed pairs (lo = column 2*i2, hi = column 2*i2+1)
 			const float *rb0 = base + 2 * (2 * i2), *rb1 = rb0 + 2;
 			const float *sa0 = s0 + (2 * i2) * 6 * 32, *sb0 = s2 + (2 * i2) * 6 * 32;             // column 2*i2:   quadrants 0 (j even), 2 (j odd)
@@ -392,6 +398,18 @@ __device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t
 		}
 		cost = ncc_cost(t, inv_w);
 	}
+	return cost;
+}
+
+template <int SPT = 4, bool ROLL = true>
+__device__ __forceinline__ float ncc6_quad(const QuadCtx &q, cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc, bool want,
+                                           const float *tile, int pitch, int lx, int ly, int px, int py, float inv_w) {
+	// must be called by all 32 lanes of the warp convergently; all 36 fetches are in flight before any result is consumed
+	NccFetch f;
+	ncc6_issue(q, tex, layer, Hm, vc, want, px, py, f);
+	ncc6_store(q, f);
+	__syncwarp();
+	const float cost = ncc6_accum<ROLL>(q, f.active, tile, pitch, lx, ly, inv_w);
 	__syncwarp();
 	return cost;
 }
