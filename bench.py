@@ -122,10 +122,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
 
-    if args.impl == "reference" and rank != 0:
-        if world > 1:
-            dist.barrier(); dist.destroy_process_group()
-        return
+    if args.impl == "reference" and world > 1:
+        dist.barrier()                 # brings NCCL up (and its banner out) before anything is printed
+        if rank != 0:                  # the reference is a single-GPU program: rank 0 alone runs it
+            dist.destroy_process_group()
+            return
 
     import parity_tools as T
     from apd_mvs_b200 import engine as E
@@ -305,7 +306,9 @@ def main():
             line["cpu_baseline"] = cpu_baseline(np, T, E)
         print(json.dumps(line))
     if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        if args.impl == "ours":
+            dist.barrier()
+        dist.destroy_process_group()
 
 
 def cpu_baseline(np, T, E):
