@@ -21,6 +21,17 @@ sc = make_scene(1010, 90, 2)
 s = P.Scene(sc["images"].numpy(), sc["cameras"], P.ring_pairs(3, 2))
 s.Run()
 print("scene", float(s.Depth(0).mean()))
+from apd_mvs_b200 import fusion as F
+import fusion_tools as FT
+fu = F.Fusion(3, 1010, 90)
+bgr = FT.colour_images(sc["images"].numpy())
+for v in range(3):
+    fu.SetView(v, bgr[v], sc["cameras"][v], s.Depth(v), s.Normal(v), s.States(v))
+for r, ss in P.ring_pairs(3, 2):
+    fu.AddProblem(r, ss)
+xyz, col = fu.RunFusion()
+print("fusion", len(xyz), fu.Timing()["max_rounds"])
+fu.close()
 s.close()
 PY
 for tool in memcheck racecheck; do
