@@ -66,6 +66,7 @@ __global__ void k_setup_views(const apd_camera *cams, int S, ViewConst *vout, Re
 		o.baseline = sqrtaf(fmaf(d2, d2, fmaf(d0, d0, d1 * d1)));
 	}
 	o.cam = sc;
+	o.pad_ = 0.0f;
 	vout[v] = o;
 }
 
