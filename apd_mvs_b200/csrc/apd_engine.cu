@@ -22,8 +22,6 @@ cudaError_t launch_strong(cudaStream_t, const Args &, int iter, int color, const
 int make_tensor_maps(const float *, int, int, CUtensorMap *, CUtensorMap *);
 void launch_depth_normal(cudaStream_t, const Args &);
 void launch_median(cudaStream_t, const Args &, int color);
-cudaError_t launch_classify(cudaStream_t, const Args &);
-cudaError_t launch_local_refine(cudaStream_t, const Args &);
 cudaError_t launch_sweep(cudaStream_t, const Args &, int mode, const CUtensorMap *);
 // deformation path (apd_kernels_weak.cu)
 cudaError_t launch_nearest_strong(cudaStream_t, const Args &);

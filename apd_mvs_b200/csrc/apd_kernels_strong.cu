@@ -6,17 +6,20 @@
 //   k_strong           K6/K7 Black/RedPixelUpdateStrong APD.cu:1547-1585 -> :982-1321 -> :837-890
 //   k_depth_normal     K11 GetDepthandNormal          APD.cu:1587-1602
 //   k_median           K12/K13 Black/RedPixelFilterStrong APD.cu:1604-1748
-//   k_classify         K14 DepthToWeak                APD.cu:1990-2144
-//   k_local_refine     K15 LocalRefine                APD.cu:2146-2232
-// Design (not a translation): one thread per pixel as in the reference, but
-//   * the reference window lives in shared memory (one tile per block, loaded once, reused by all
-//     14*S NCC evaluations of a pixel) instead of a second texture fetch per tap;
-//   * source views are layers of ONE layered texture (uniform handle, per-view layer index);
-//   * all camera algebra that does not depend on the hypothesis is precomputed per view and read
-//     from shared memory, the 6x6 tap loop is fully unrolled so 36 texture fetches are in flight
-//     per thread, the 8xS cost matrix sits in shared memory (no local-memory stack), the RNG
-//     state is loaded/stored once per kernel (24 B instead of 48 B), views with zero sampling
-//     weight are skipped in the 6 post-selection evaluations (their weight multiplies them by 0);
+//   k_sweep            K14 DepthToWeak + K15 LocalRefine (fused)  APD.cu:1990-2144, 2146-2232
+// Design (not a translation):
+//   * every NCC evaluation is fetched by the four lanes of a quad (each takes a 3x3 quadrant of the 6x6 window, so a
+//     texture instruction covers 2x2 clusters of neighbouring taps), staged through a per-warp shared-memory slab, and
+//     accumulated by its owner lane in the reference's order (ncc6_quad, apd_device.cuh);
+//   * the reference window lives in shared memory (one tile + halo per block, loaded by TMA from a replicated-border
+//     copy of the image) and its sum / sum of squares are computed once per pixel;
+//   * source views are layers of ONE layered texture (uniform handle, per-lane layer index), so lanes walk their own
+//     lists of sampled views;
+//   * all camera algebra that does not depend on the hypothesis is precomputed per view and read from shared memory;
+//     the 8xS cost matrices and the K14 profile sit in a slab pool indexed by resident block (L1/L2, not shared memory,
+//     which would come out of the L1 the texture fetches live on); the RNG state is loaded/stored once per kernel;
+//   * work that cannot change the result is skipped exactly (zero-weight views, hypotheses that can no longer win,
+//     profile entries the classification never reads);
 //   * no host synchronisation between launches.
 #include <curand_kernel.h>
 #include <cuda.h>
@@ -664,96 +667,6 @@ __device__ __forceinline__ float sweep_cost(const Args &a, const RefConst &rc, c
 	return acc;
 }
 
-// K14: reliable-pixel classification
-__global__ void __launch_bounds__(kFullNT) k_classify(const Args a) {
-	using C = TileCfg<kFullTW, kFullTH>;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	float *tile = reinterpret_cast<float *>(smem_raw);
-	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
-	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
-	float *prof = reinterpret_cast<float *>(sv + a.S);        // [61][NT] cost profile
-	const int tid = threadIdx.y * kFullTW + threadIdx.x;
-	const int x0 = blockIdx.x * kFullTW, y0 = blockIdx.y * kFullTH;
-	load_tile<kFullTW, kFullTH, kFullNT>(a, tile, x0, y0, tid);
-	load_views(a, sv, sr, tid, kFullNT);
-	__syncthreads();
-	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
-	if (px >= a.W || py >= a.H) return;
-	const size_t center = (size_t)py * a.W + px;
-	if (px < 6 || py < 6 || px >= a.W - 6 || py >= a.H - 6) { a.states[center] = APD_UNKNOWN; return; }
-	const RefConst &rc = *sr;
-	const uint32_t bits = a.sel_views[center];
-	const VW vw = vw_load(a.view_w, center);
-	SweepCtx c;
-	if (!sweep_setup(a, rc, sv, center, bits, vw, c) || c.valid == 0) { a.states[center] = APD_UNKNOWN; return; }
-	const float inv_wn = rcpf(c.weight_normal);
-	float *p = prof + tid;
-	for (int k = -30; k <= 30; ++k) {
-		const float d = c.kb * rcpf(c.disp + (float)k);
-		float pc = 2.0f;
-		if (!(d < a.depth_min || d > a.depth_max)) {
-			pc = sweep_cost<false>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, d) * inv_wn;
-			pc = (2.0f > pc) ? pc : 2.0f;       // OpenCV MIN(2.0f, p_cost)
-		}
-		p[(k + 30) * kFullNT] = pc;
-	}
-	// peak analysis, APD.cu:2092-2143
-	int peak_count = 0, min_peak = 0; float min_cost = 2.0f;
-	unsigned long long peaks = 0ull;
-	for (int i = 2; i < 59; ++i) {
-		const float ci = p[i * kFullNT];
-		if (p[(i - 1) * kFullNT] > ci && p[(i + 1) * kFullNT] > ci) {
-			peaks |= 1ull << i; peak_count++;
-			if (ci < min_cost) { min_peak = i; min_cost = ci; }
-		}
-	}
-	uint8_t out;
-	if (abs(min_peak - 30) > a.weak_peak_radius || p[min_peak * kFullNT] > 0.5f) out = APD_WEAK;
-	else if (peak_count == 1) out = (p[min_peak * kFullNT] <= 0.15f) ? APD_STRONG : APD_WEAK;
-	else {
-		float var = 0.0f;
-		for (int i = 2; i < 59; ++i) if (((peaks >> i) & 1ull) && i != min_peak) { const float d = p[i * kFullNT] - min_cost; var = fmaf(d, d, var); }
-		var = sqrtaf(var) * rcpf((float)(peak_count - 1));
-		out = (var > 0.2f) ? APD_STRONG : APD_WEAK;
-	}
-	a.states[center] = out;
-}
-
-// K15
-__global__ void __launch_bounds__(kFullNT) k_local_refine(const Args a) {
-	using C = TileCfg<kFullTW, kFullTH>;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	float *tile = reinterpret_cast<float *>(smem_raw);
-	RefConst *sr = reinterpret_cast<RefConst *>(tile + C::ELEMS);
-	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
-	const int tid = threadIdx.y * kFullTW + threadIdx.x;
-	const int x0 = blockIdx.x * kFullTW, y0 = blockIdx.y * kFullTH;
-	load_tile<kFullTW, kFullTH, kFullNT>(a, tile, x0, y0, tid);
-	load_views(a, sv, sr, tid, kFullNT);
-	__syncthreads();
-	const int px = x0 + threadIdx.x, py = y0 + threadIdx.y;
-	if (px >= a.W || py >= a.H) return;
-	const size_t center = (size_t)py * a.W + px;
-	const RefConst &rc = *sr;
-	const uint32_t bits = a.sel_views[center];
-	const VW vw = vw_load(a.view_w, center);
-	SweepCtx c;
-	if (!sweep_setup(a, rc, sv, center, bits, vw, c)) return;
-	if (c.weight_normal == 0.0f || c.valid == 0) return;
-	// cost of the current depth, APD.cu:2176-2182 (K14's accumulation form)
-	const float cost_sum = sweep_cost<false, true>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, c.depth);
-	const float inv_wn = rcpf(c.weight_normal);
-	float min_cost = 2.0f, best_depth = c.depth;
-	for (int k = -5; k <= 5; ++k) {
-		const float d = c.kb * rcpf(c.disp + (float)k);
-		if (d < a.depth_min || d > a.depth_max) continue;
-		const float tc = sweep_cost<true>(a, rc, sv, tile, C::PW, threadIdx.x, threadIdx.y, px, py, c, bits, vw, d) * inv_wn;
-		if (tc < min_cost) { min_cost = tc; best_depth = d; }
-	}
-	const float diff = fmaf(inv_wn, cost_sum, -min_cost);   // (cost_now / weight_normal) - min_cost, one FFMA
-	if ((double)diff > 0.1) a.planes[center].w = best_depth;
-}
-
 // ------------------------------------------------------------------------------------------------
 // K14 + K15 fused (used by full runs). LocalRefine's 11 disparity steps are the centre of DepthToWeak's
 // 61-step sweep: same planes, same NCC values (and the same geometric term), only the weighted
@@ -984,14 +897,6 @@ void launch_median(cudaStream_t st, const Args &a, int color) {
 	dim3 b(32, 8), g((a.W + 31) / 32, ((a.H + 1) / 2 + 7) / 8);
 	k_median<<<g, b, 0, st>>>(a, color);
 }
-cudaError_t launch_classify(cudaStream_t st, const Args &a) {
-	using C = TileCfg<kFullTW, kFullTH>;
-	const size_t smem = C::ELEMS * 4 + smem_common(a.S) + (size_t)61 * kFullNT * 4;
-	cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
-	k_classify<<<g, b, smem, st>>>(a);
-	return cudaGetLastError();
-}
 // mode 0: K14 only, 1: K15 only, 2: K14+K15 fused
 cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode, const CUtensorMap *tmap) {
 	using C = TileCfg<kSweepTW, kSweepTH>;
@@ -1002,14 +907,6 @@ cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode, const CUtenso
 	if (coop) { if (mode == 0) SWEEP_LAUNCH(true, false, true); else if (mode == 1) SWEEP_LAUNCH(false, true, true); else SWEEP_LAUNCH(true, true, true); }
 	else { if (mode == 0) SWEEP_LAUNCH(true, false, false); else if (mode == 1) SWEEP_LAUNCH(false, true, false); else SWEEP_LAUNCH(true, true, false); }
 #undef SWEEP_LAUNCH
-	return cudaGetLastError();
-}
-cudaError_t launch_local_refine(cudaStream_t st, const Args &a) {
-	using C = TileCfg<kFullTW, kFullTH>;
-	const size_t smem = C::ELEMS * 4 + smem_common(a.S);
-	cudaFuncSetAttribute(k_local_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	dim3 b(kFullTW, kFullTH), g((a.W + kFullTW - 1) / kFullTW, (a.H + kFullTH - 1) / kFullTH);
-	k_local_refine<<<g, b, smem, st>>>(a);
 	return cudaGetLastError();
 }
 
