@@ -229,33 +229,6 @@ __device__ __forceinline__ float src_tap(cudaTextureObject_t tex, int layer, con
 	return tex2DLayered<float>(tex, fmaf(xs, rz, 0.5f), fmaf(ys, rz, 0.5f), layer);
 }
 
-// ComputeBilateralNCCOld (APD.cu:530-614) for the pixel at tile-local (lx, ly): 6x6 taps at
-// offsets {-5,-3,-1,1,3,5}^2, x-offset outer / y-offset inner, row sums folded into totals.
-// `tile` points at the shared-memory copy of the reference image, tile[(ly+5+j)*pitch + lx+5+i].
-template <int RADIUS, int INC>
-__device__ __forceinline__ float ncc_strong(cudaTextureObject_t tex, int layer, const Homog &Hm, const ViewConst &vc,
-                                            const float *tile, int pitch, int lx, int ly, int px, int py, float inv_w) {
-	if (!centre_inside(Hm, vc, (float)px, (float)py)) return kCostMax;
-	const float *h = Hm.h;
-	NccSums t = {0.f, 0.f, 0.f, 0.f, 0.f};
-	const float *base = tile + (ly + kHalo) * pitch + (lx + kHalo);
-#pragma unroll
-	for (int i = -RADIUS; i <= RADIUS; i += INC) {
-		const float xf = (float)(px + i);
-		const float ax = h[0] * xf, ay = h[3] * xf, az = h[6] * xf;
-		NccSums r = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-		for (int j = -RADIUS; j <= RADIUS; j += INC) {
-			const float rp = base[j * pitch + i];
-			const float sp = src_tap(tex, layer, h, ax, ay, az, (float)(py + j));
-			r.r += rp; r.rr = fmaf(rp, rp, r.rr); r.rs = fmaf(rp, sp, r.rs);
-			r.s += sp; r.ss = fmaf(sp, sp, r.ss);
-		}
-		t.r += r.r; t.rr += r.rr; t.s += r.s; t.ss += r.ss; t.rs += r.rs;
-	}
-	return ncc_cost(t, inv_w);
-}
-
 // ---- quad-cooperative NCC ------------------------------------------------------------------------
 // Measured on B200 (tools/tex_probe3.cu, profiles/): the texture data pipe delivers the full
 // 4 bilinear fetches/clk/SM only when the four lanes of a quad touch a compact (<= ~4x4 texel)

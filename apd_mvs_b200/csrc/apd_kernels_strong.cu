@@ -635,37 +635,6 @@ __device__ __forceinline__ bool sweep_setup(const Args &a, const RefConst &rc, c
 }
 
 // weighted multi-view cost of the pixel's plane moved to depth `d` (APD.cu:2067-2081)
-template <bool K15_FORM, bool HOISTED_Z = false>
-__device__ __forceinline__ float sweep_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float *tile, int pitch,
-                                            int lx, int ly, int px, int py, const SweepCtx &c, uint32_t bits, const VW &vw, float d) {
-	const float xf = (float)px, yf = (float)py;
-	const float inv36 = a.inv_w[0];
-	float4 t = c.pl;
-	if (HOISTED_Z) {
-		// LocalRefine's first loop (APD.cu:2173-2177): the compiler hoists normal.z * depth out of the
-		// view loop as a rounded product, so the plane offset there is -((d*nz) + fma(X0,nx,X1*ny))
-		float X0, X1; backproject(rc, xf, yf, d, X0, X1);
-		t.w = -((d * t.z) + fmaf(X0, t.x, X1 * t.y));
-	} else {
-		t.w = plane_offset(rc, xf, yf, d, t.x, t.y, t.z);
-	}
-	float acc = 0.0f;
-	for (int v = 0; v < a.S; ++v) {
-		if (!((bits >> v) & 1u)) continue;
-		const int w = vw_get(vw, v);
-		if (w == 0) continue;                    // multiplied by a zero weight in the reference
-		const Homog Hm = make_homography(rc, sv[v], t);
-		float tc = ncc_strong<5, 2>(a.img_tex, v + 1, Hm, sv[v], tile, pitch, lx, ly, px, py, inv36);
-		if (K15_FORM) {   // APD.cu:2217-2220
-			acc = fmaf((float)w, tc, acc);
-			if (a.geom) acc = fmaf((float)w, a.geom_factor * geom_cost(a, rc, sv[v], v + 1, t, xf, yf), acc);
-		} else {          // APD.cu:2074-2078
-			if (a.geom) tc = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, t, xf, yf), tc);
-			acc = fmaf((float)w, tc, acc);
-		}
-	}
-	return acc;
-}
 
 // ------------------------------------------------------------------------------------------------
 // K14 + K15 fused (used by full runs). LocalRefine's 11 disparity steps are the centre of DepthToWeak's
@@ -676,7 +645,7 @@ __device__ __forceinline__ float sweep_cost(const Args &a, const RefConst &rc, c
 // fusion is exact. All threads stay in the loops: fetches are quad-cooperative (ncc6_quad).
 constexpr int kSweepTW = 16, kSweepTH = 8, kSweepNT = 128;
 
-template <bool DO14, bool DO15, bool COOP>
+template <bool DO14, bool DO15>
 __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __grid_constant__ CUtensorMap tmap) {
 	using C = TileCfg<kSweepTW, kSweepTH>;
 	extern __shared__ __align__(128) unsigned char smem_raw[];      // no static smem in this kernel: the TMA destination must be 128-B aligned
@@ -762,8 +731,7 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 			m &= m - 1u;
 			const int w = vw_get(vw, v);
 			float ncc = kCostMax;
-			if (COOP) ncc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
-			else if (want) ncc = ncc_strong<5, 2>(a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], tile, C::PW, lx, ly, px, py, inv36);
+			ncc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
 			if (want) {
 				float g = 0.0f;
 				if (a.geom) g = geom_cost(a, rc, sv[v], v + 1, t, xf, yf);
@@ -813,8 +781,7 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 			m &= m - 1u;
 			const int w = vw_get(vw, v);
 			float tc = kCostMax;
-			if (COOP) tc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
-			else if (want) tc = ncc_strong<5, 2>(a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], tile, C::PW, lx, ly, px, py, inv36);
+			tc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
 			if (want) {
 				if (a.geom) tc = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, t, xf, yf), tc);
 				cost_sum = fmaf((float)w, tc, cost_sum);
@@ -902,10 +869,8 @@ cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode, const CUtenso
 	using C = TileCfg<kSweepTW, kSweepTH>;
 	const size_t smem = C::ELEMS * 4 + 16 + (kSweepNT / 32) * kPatchFloats * 4 + smem_common(a.S);
 	dim3 b(kSweepTW, kSweepTH), g((a.W + kSweepTW - 1) / kSweepTW, (a.H + kSweepTH - 1) / kSweepTH);
-	static const bool coop = getenv("APD_SWEEP_SIMPLE") == nullptr;   // cooperative fetch is the default (A/B measured: 16.9 vs 22.4 ms)
-#define SWEEP_LAUNCH(A, B, Cc) do { cudaFuncSetAttribute(k_sweep<A, B, Cc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_sweep<A, B, Cc><<<g, b, smem, st>>>(a, *tmap); } while (0)
-	if (coop) { if (mode == 0) SWEEP_LAUNCH(true, false, true); else if (mode == 1) SWEEP_LAUNCH(false, true, true); else SWEEP_LAUNCH(true, true, true); }
-	else { if (mode == 0) SWEEP_LAUNCH(true, false, false); else if (mode == 1) SWEEP_LAUNCH(false, true, false); else SWEEP_LAUNCH(true, true, false); }
+#define SWEEP_LAUNCH(A, B) do { cudaFuncSetAttribute(k_sweep<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_sweep<A, B><<<g, b, smem, st>>>(a, *tmap); } while (0)
+	if (mode == 0) SWEEP_LAUNCH(true, false); else if (mode == 1) SWEEP_LAUNCH(false, true); else SWEEP_LAUNCH(true, true);
 #undef SWEEP_LAUNCH
 	return cudaGetLastError();
 }
