@@ -545,47 +545,51 @@ __global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, 
 		for (int k = 1; k < 8; ++k) if (fc[k] <= best_cost) { best_cost = fc[k]; best_k = k; }
 	}
 
+	// One loop (and one inlined copy of the deformable NCC: the instruction cache is a measured limiter of this kernel)
+	// over the pixel's plane evaluations: h = -1 the current plane, h = 0 the fit plane, h = 1..5 the five hypotheses of
+	// PlaneHypothesisRefinementWeak (APD.cu:892-980), which returns before any draw when the fit plane is all-zero.
 	float4 pl_now = a.planes[center];
-	float cost_now = weak_cost(a, rc, sv, pl_now, an, rcol, vw, px, py, inv36, inv9, inv_wn, __int_as_float(0x7f800000)) * inv_wn;
-	const float cost_stored = cost_now;
-	float depth_now = plane_depth(rc, pl_now, xf, yf);
-	if ((flags >> best_k) & 1u) {
-		int bp = pos[0];
-#pragma unroll
-		for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
-		const float4 cand = a.planes[bp];
-		const float d = plane_depth(rc, cand, xf, yf);
-		if (d >= a.depth_min && d <= a.depth_max && best_cost < cost_now) {
-			depth_now = d; pl_now = cand; cost_now = best_cost; a.sel_views[center] = temp_sel;
-		}
-	}
-	// PlaneHypothesisRefinementWeak, APD.cu:892-980
-	{
-		const float4 fit = a.fit_planes[center];
-		if (!(fit.x == 0.0f && fit.y == 0.0f && fit.z == 0.0f)) {
-			{
-				const float d = plane_depth(rc, fit, xf, yf);
-				if (d >= a.depth_min && d <= a.depth_max) {      // an out-of-range plane is never adopted: not evaluated
-					const float tc = weak_cost(a, rc, sv, fit, an, rcol, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
-					if (tc < cost_now) { depth_now = d; pl_now = fit; cost_now = tc; }
-				}
-			}
-			const float depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
-			const float4 n_rand = random_normal(rc, xf, yf, rng, depth_now);
-			const float lo = depth_now * (1.0f - 0.02f);
-			const float span = fmaf(depth_now, 1.0f + 0.02f, -lo);
-			const float depth_pert = fmaf(span, rng_uniform(rng), lo);
-			const float4 n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
-			const float4 n0 = pl_now; const float d0 = depth_now;
+	float cost_now = 0.0f, cost_stored = 0.0f, depth_now = 0.0f;
+	const float4 fit = a.fit_planes[center];
+	const bool have_fit = !(fit.x == 0.0f && fit.y == 0.0f && fit.z == 0.0f);
+	float depth_rand = 0.0f, depth_pert = 0.0f, d0 = 0.0f;
+	float4 n_rand = pl_now, n_pert = pl_now, n0 = pl_now;
 #pragma unroll 1
-			for (int i = 0; i < 5; ++i) {
-				const float di = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : d0);
-				float4 t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
-				t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
-				const float d = plane_depth(rc, t, xf, yf);
-				if (d >= a.depth_min && d <= a.depth_max) {
-					const float tc = weak_cost(a, rc, sv, t, an, rcol, vw, px, py, inv36, inv9, inv_wn, cost_now) * inv_wn;
-					if (tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+	for (int h = -1; h < (have_fit ? 6 : 0); ++h) {
+		float4 t = pl_now; float d = 0.0f; bool in_range = true;
+		if (h == 0) { t = fit; d = plane_depth(rc, t, xf, yf); in_range = d >= a.depth_min && d <= a.depth_max; }
+		else if (h > 0) {
+			if (h == 1) {
+				depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
+				n_rand = random_normal(rc, xf, yf, rng, depth_now);
+				const float lo = depth_now * (1.0f - 0.02f);
+				const float span = fmaf(depth_now, 1.0f + 0.02f, -lo);
+				depth_pert = fmaf(span, rng_uniform(rng), lo);
+				n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
+				n0 = pl_now; d0 = depth_now;
+			}
+			const int i = h - 1;
+			const float di = (i == 0 || i == 2) ? depth_rand : (i == 4 ? depth_pert : d0);
+			t = (i == 1 || i == 2) ? n_rand : (i == 3 ? n_pert : n0);
+			t.w = plane_offset(rc, xf, yf, di, t.x, t.y, t.z);
+			d = plane_depth(rc, t, xf, yf);
+			in_range = d >= a.depth_min && d <= a.depth_max;
+		}
+		if (!in_range) continue;                 // an out-of-range plane is never adopted: not evaluated
+		const float tc = weak_cost(a, rc, sv, t, an, rcol, vw, px, py, inv36, inv9, inv_wn, h < 0 ? __int_as_float(0x7f800000) : cost_now) * inv_wn;
+		if (h >= 0) {
+			if (tc < cost_now) { depth_now = d; pl_now = t; cost_now = tc; }
+		} else {
+			cost_now = tc; cost_stored = tc;
+			depth_now = plane_depth(rc, pl_now, xf, yf);
+			if ((flags >> best_k) & 1u) {
+				int bp = pos[0];
+#pragma unroll
+				for (int k = 1; k < 8; ++k) if (best_k == k) bp = pos[k];
+				const float4 cand = a.planes[bp];
+				const float dc = plane_depth(rc, cand, xf, yf);
+				if (dc >= a.depth_min && dc <= a.depth_max && best_cost < cost_now) {
+					depth_now = dc; pl_now = cand; cost_now = best_cost; a.sel_views[center] = temp_sel;
 				}
 			}
 		}
