@@ -420,7 +420,7 @@ __device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *s
 
 constexpr int kWeakTW = 32, kWeakTH = 8;      // 128 pixels of one colour per block
 
-__global__ void __launch_bounds__(kWeakNT) k_weak(const Args a, const int iter, const int color) {
+__global__ void __launch_bounds__(kWeakNT, 3) k_weak(const Args a, const int iter, const int color) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	RefConst *sr = reinterpret_cast<RefConst *>(smem_raw);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
