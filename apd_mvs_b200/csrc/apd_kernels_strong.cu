@@ -852,6 +852,9 @@ cudaError_t launch_strong(cudaStream_t st, const Args &a, int iter, int color, c
 	const size_t smem = C::ELEMS * 4 + 16 + (NT / 32) * kPatchFloats * 4 + smem_common(a.S);
 	if (smem > 227 * 1024) return cudaErrorInvalidValue;
 	cudaFuncSetAttribute(k_strong<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	// four resident blocks need 4 x 25.5 KB: ask for the 100 KB shared-memory configuration (the driver would take 132 KB), the
+	// difference goes to the L1 the texture fetches live on
+	if (4 * (smem + 1024) <= 100 * 1024) cudaFuncSetAttribute(k_strong<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 43);
 	dim3 g((a.W + kHalfTW - 1) / kHalfTW, (a.H + kHalfTH - 1) / kHalfTH);
 	k_strong<NT><<<g, NT, smem, st>>>(a, iter, color, *tmap);
 	return cudaGetLastError();
@@ -869,7 +872,9 @@ cudaError_t launch_sweep(cudaStream_t st, const Args &a, int mode, const CUtenso
 	using C = TileCfg<kSweepTW, kSweepTH>;
 	const size_t smem = C::ELEMS * 4 + 16 + (kSweepNT / 32) * kPatchFloats * 4 + smem_common(a.S);
 	dim3 b(kSweepTW, kSweepTH), g((a.W + kSweepTW - 1) / kSweepTW, (a.H + kSweepTH - 1) / kSweepTH);
-#define SWEEP_LAUNCH(A, B) do { cudaFuncSetAttribute(k_sweep<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_sweep<A, B><<<g, b, smem, st>>>(a, *tmap); } while (0)
+#define SWEEP_LAUNCH(A, B) do { cudaFuncSetAttribute(k_sweep<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+		if (4 * (smem + 1024) <= 100 * 1024) cudaFuncSetAttribute(k_sweep<A, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 43); \
+		k_sweep<A, B><<<g, b, smem, st>>>(a, *tmap); } while (0)
 	if (mode == 0) SWEEP_LAUNCH(true, false); else if (mode == 1) SWEEP_LAUNCH(false, true); else SWEEP_LAUNCH(true, true);
 #undef SWEEP_LAUNCH
 	return cudaGetLastError();
