@@ -10,6 +10,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include "apd_device.cuh"
 #include "apd_engine_internal.h"
 
@@ -25,10 +26,14 @@ void launch_median(cudaStream_t, const Args &, int color);
 cudaError_t launch_sweep(cudaStream_t, const Args &, int mode, const CUtensorMap *);
 // deformation path (apd_kernels_weak.cu)
 cudaError_t launch_nearest_strong(cudaStream_t, const Args &);
-cudaError_t launch_gen_anchors(cudaStream_t, const Args &);
+cudaError_t launch_gen_anchors(cudaStream_t, const Args &, void *anchor_consts);
+size_t anchor_consts_bytes();
 cudaError_t launch_demote_unreliable(cudaStream_t, const Args &);
 cudaError_t launch_fit_plane(cudaStream_t, const Args &);
 cudaError_t launch_weak(cudaStream_t, const Args &, int iter, int color);
+// quad-per-pixel WEAK propagation over compacted lists (apd_kernels_weakq.cu)
+cudaError_t launch_weak_lists(cudaStream_t, const Args &, bool split);
+cudaError_t launch_weak_q(cudaStream_t, const Args &, int iter, int color, int work_slot, int num_sms);
 }  // namespace apd
 
 using namespace apd;
@@ -58,12 +63,16 @@ static int check_params(apd_handle h, const apd_params *p) {
 	if (p->state < APD_FIRST_INIT || p->state > APD_REFINE_ITER) return fail(h, APD_E_ARG, "bad state");
 	if (p->rotate_time < 1 || p->rotate_time > 4) return fail(h, APD_E_ARG, "rotate_time must be 1..4 (APD.cu:1790)");
 	if (p->top_k < 1) return fail(h, APD_E_ARG, "top_k must be >= 1");
+	// k_sweep evaluates profile entries 1..59 around a centre window of at most 29 steps; the reference's peak rules
+	// (APD.cu:2092-2143) match it for radii up to 28 (main.cpp uses 2..6)
+	if (p->weak_peak_radius < 0 || p->weak_peak_radius > 28) return fail(h, APD_E_LIMIT, "weak_peak_radius must be 0..28");
 	return APD_OK;
 }
 
 static int make_layered(apd_handle h, cudaArray_t *arr, cudaTextureObject_t *tex) {
 	cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
-	CKH(cudaMalloc3DArray(arr, &desc, make_cudaExtent(h->W, h->H, h->N), cudaArrayLayered));
+	// h->capacity layers, not the current image count: a later problem of the same round may have more source views
+	CKH(cudaMalloc3DArray(arr, &desc, make_cudaExtent(h->W, h->H, h->capacity), cudaArrayLayered));
 	cudaResourceDesc res; memset(&res, 0, sizeof(res));
 	res.resType = cudaResourceTypeArray; res.res.array.array = *arr;
 	cudaTextureDesc td; memset(&td, 0, sizeof(td));
@@ -111,6 +120,17 @@ extern "C" int apd_create(apd_handle *out, int device, int width, int height, in
 		ALLOC(h->scratch, (size_t)kSlabSMs * kSlabPerSM * h->slab_stride * 4);
 		ALLOC(h->slab_slots, (size_t)kSlabSMs * kSlabPerSM * 4);
 	}
+	h->wlist_stride = (int)(((n + 1) / 2 + 63) / 64 * 64);
+	ALLOC(h->wlist, (size_t)2 * h->wlist_stride * sizeof(int));
+	ALLOC(h->wctrl, (size_t)(kWorkBase + kWorkSlots) * sizeof(int));
+	ALLOC(h->anchor_consts, anchor_consts_bytes());
+	{
+		int sms = 0;
+		if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 1) return bail(APD_E_CUDA);
+		h->num_sms = sms;
+		const char *w = getenv("APD_WEAK_IMPL");
+		h->weak_impl = (w && !strcmp(w, "old")) ? 0 : 1;
+	}
 #undef ALLOC
 	if (make_layered(h, &h->img_arr, &h->img_tex) != APD_OK) return bail(APD_E_CUDA);
 	if (make_tensor_maps(h->ref_pad, h->ref_pitch, h->ref_rows, &h->tmap_strong, &h->tmap_sweep) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return bail(APD_E_CUDA); }
@@ -135,7 +155,7 @@ extern "C" void apd_destroy(apd_handle h) {
 	if (h->img_arr) cudaFreeArray(h->img_arr);
 	if (h->depth_arr) cudaFreeArray(h->depth_arr);
 	void *ptrs[] = {h->ref_lin, h->ref_pad, h->d_cams, h->d_views, h->d_ref, h->d_invw, h->planes, h->fit_planes, h->prior_planes,
-	                h->costs, h->sel_views, h->prior_views, h->states, h->prior_states, h->reliable, h->rng, h->view_w, h->anchors, h->nearest, h->scratch, h->slab_slots};
+	                h->costs, h->sel_views, h->prior_views, h->states, h->prior_states, h->reliable, h->rng, h->view_w, h->anchors, h->nearest, h->scratch, h->slab_slots, h->wlist, h->wctrl, h->anchor_consts};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
@@ -264,6 +284,7 @@ static Args make_args(apd_handle h) {
 	a.planes = h->planes; a.fit_planes = h->fit_planes; a.costs = h->costs;
 	a.sel_views = h->sel_views; a.states = h->states; a.rng = h->rng; a.view_w = h->view_w;
 	a.anchors = h->anchors; a.nearest = h->nearest; a.reliable = h->reliable; a.scratch = h->scratch; a.slab_slots = h->slab_slots; a.slab_stride = h->slab_stride;
+	a.wlist = h->wlist; a.wlist_stride = h->wlist_stride; a.wctrl = h->wctrl;
 	return a;
 }
 
@@ -296,6 +317,10 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	}
 	CKH(cudaMemsetAsync(h->fit_planes, 0, n * 16, st));                            // APD.cpp:651
 	CKH(cudaMemsetAsync(h->slab_slots, 0, (size_t)kSlabSMs * kSlabPerSM * 4, st));  // all slabs free
+	CKH(cudaMemsetAsync(h->wctrl, 0, (size_t)(kWorkBase + kWorkSlots) * sizeof(int), st));
+	// the reference allocates these per run (APD.cpp:645-649): pixels no update reaches must not see the previous run's values
+	CKH(cudaMemsetAsync(h->view_w, 0, n * 16, st));
+	CKH(cudaMemsetAsync(h->costs, 0, n * 4, st));
 	launch_setup_views(st, h->d_cams, h->S, h->d_views, h->d_ref, h->d_invw); h->launches++;
 	CKH(cudaGetLastError());
 
@@ -303,16 +328,21 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	CKH(cudaEventRecord(h->events[0], st));
 #define STAGE_END() do { CKH(cudaGetLastError()); CKH(cudaEventRecord(h->events[stage + 1], st)); if (stage == stage_end) goto done; ++stage; } while (0)
 	launch_rng_seed(st, a, h->seed); h->launches++; STAGE_END();                                          // 0  K1
-	if (apd_on) { CKH(launch_nearest_strong(st, a)); h->launches++; } STAGE_END();                         // 1  K2
-	if (apd_on) { CKH(launch_gen_anchors(st, a)); h->launches++; } STAGE_END();                            // 2  K3
-	if (apd_on) { CKH(launch_demote_unreliable(st, a)); h->launches++; } STAGE_END();                      // 3  K4
+	if (apd_on) { CKH(launch_nearest_strong(st, a)); h->launches += 2; } STAGE_END();                         // 1  K2
+	if (apd_on) { CKH(launch_gen_anchors(st, a, h->anchor_consts)); h->launches += 2; } STAGE_END();        // 2  K3
+	if (apd_on) {                                                                                          // 3  K4 (+ the WEAK lists K9/K10 walk)
+		CKH(launch_demote_unreliable(st, a)); h->launches++;
+		if (h->weak_impl == 1) { CKH(launch_weak_lists(st, a, true)); h->launches++; }
+	}
+	STAGE_END();
 	CKH(launch_init_planes(st, a)); h->launches++; STAGE_END();                                            // 4  K5
 	for (int it = 0; it < p.max_iterations; ++it) {
 		CKH(launch_strong(st, a, it, 0, &h->tmap_strong)); h->launches++; STAGE_END();                                      // K6
 		CKH(launch_strong(st, a, it, 1, &h->tmap_strong)); h->launches++; STAGE_END();                                      // K7
 		if (apd_on) { CKH(launch_fit_plane(st, a)); h->launches++; } STAGE_END();                          // K8
-		if (apd_on) { CKH(launch_weak(st, a, it, 0)); h->launches++; } STAGE_END();                        // K9
-		if (apd_on) { CKH(launch_weak(st, a, it, 1)); h->launches++; } STAGE_END();                        // K10
+		const int slot = (2 * it) % kWorkSlots;
+		if (apd_on) { CKH(h->weak_impl == 1 ? launch_weak_q(st, a, it, 0, slot, h->num_sms) : launch_weak(st, a, it, 0)); h->launches++; } STAGE_END();        // K9
+		if (apd_on) { CKH(h->weak_impl == 1 ? launch_weak_q(st, a, it, 1, slot + 1, h->num_sms) : launch_weak(st, a, it, 1)); h->launches++; } STAGE_END();    // K10
 	}
 	launch_depth_normal(st, a); h->launches++; STAGE_END();                                                // K11
 	launch_median(st, a, 0); h->launches++; STAGE_END();                                                   // K12

@@ -26,6 +26,10 @@ struct apd_engine {
 	uint2 *rng = nullptr; uint4 *view_w = nullptr;
 	short2 *anchors = nullptr, *nearest = nullptr;
 	float *scratch = nullptr; int *slab_slots = nullptr; int slab_stride = 0;
+	int *wlist = nullptr, *wctrl = nullptr; int wlist_stride = 0;      // compacted WEAK-pixel lists (apd_kernels_weakq.cu)
+	void *anchor_consts = nullptr;                                     // K3's rotation constants, one set per handle
+	int num_sms = 0;
+	int weak_impl = 1;                                                 // 1 = quad-per-pixel k_weak_q, 0 = first design (APD_WEAK_IMPL=old)
 	CUtensorMap tmap_strong, tmap_sweep;
 	bool have_images = false, have_cams = false, have_depths = false, have_planes = false, have_states = false;
 	std::vector<cudaEvent_t> events;

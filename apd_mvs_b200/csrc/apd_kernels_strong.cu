@@ -581,39 +581,6 @@ __global__ void k_median(const Args a, const int color) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// ComputeGeomConsistencyCost, APD.cu:752-789
-__device__ __forceinline__ float geom_cost(const Args &a, const RefConst &rc, const ViewConst &vc, int layer, const float4 pl, float xf, float yf) {
-	const float depth = plane_depth(rc, pl, xf, yf);
-	float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
-	const float *R = rc.cam.R;
-	float Px = rc.cam.c[0] + fmaf(R[6], depth, fmaf(R[0], X0, R[3] * X1));
-	float Py = rc.cam.c[1] + fmaf(R[7], depth, fmaf(R[1], X0, R[4] * X1));
-	float Pz = rc.cam.c[2] + fmaf(R[8], depth, fmaf(R[2], X0, R[5] * X1));
-	const apd_camera &s = vc.cam;
-	float tx = s.t[0] + fmaf(s.R[2], Pz, fmaf(s.R[0], Px, s.R[1] * Py));
-	float ty = s.t[1] + fmaf(s.R[5], Pz, fmaf(s.R[3], Px, s.R[4] * Py));
-	float tz = s.t[2] + fmaf(s.R[8], Pz, fmaf(s.R[6], Px, s.R[7] * Py));
-	float rd = rcpf(fmaf(s.K[8], tz, fmaf(s.K[6], tx, s.K[7] * ty)));
-	float sx = fmaf(s.K[2], tz, fmaf(s.K[0], tx, s.K[1] * ty)) * rd;
-	float sy = fmaf(s.K[5], tz, fmaf(s.K[3], tx, s.K[4] * ty)) * rd;
-	const float sd = tex2DLayered<float>(a.depth_tex, (float)(int)sx + 0.5f, (float)(int)sy + 0.5f, layer);
-	if (sd == 0.0f) return 3.0f;
-	const float rsK0 = rcpf(s.K[0]), rsK4 = rcpf(s.K[4]);
-	float Y0 = (sd * (sx - s.K[2])) * rsK0;
-	float Y1 = (sd * (sy - s.K[5])) * rsK4;
-	float Qx = s.c[0] + fmaf(s.R[6], sd, fmaf(s.R[0], Y0, s.R[3] * Y1));
-	float Qy = s.c[1] + fmaf(s.R[7], sd, fmaf(s.R[1], Y0, s.R[4] * Y1));
-	float Qz = s.c[2] + fmaf(s.R[8], sd, fmaf(s.R[2], Y0, s.R[5] * Y1));
-	const float *K = rc.cam.K; const float *t = rc.cam.t;
-	float ux = t[0] + fmaf(R[2], Qz, fmaf(R[0], Qx, R[1] * Qy));
-	float uy = t[1] + fmaf(R[5], Qz, fmaf(R[3], Qx, R[4] * Qy));
-	float uz = t[2] + fmaf(R[8], Qz, fmaf(R[6], Qx, R[7] * Qy));
-	float rb = rcpf(fmaf(K[8], uz, fmaf(K[6], ux, K[7] * uy)));
-	float dc = fmaf(-fmaf(K[2], uz, fmaf(K[0], ux, K[1] * uy)), rb, xf);
-	float dr = fmaf(-fmaf(K[5], uz, fmaf(K[3], ux, K[4] * uy)), rb, yf);
-	return fminf(sqrtaf(fmaf(dc, dc, dr * dr)), 3.0f);
-}
-
 // Shared front end of K14 and K15: plane back into the reference camera frame, mean baseline and
 // summed weights over the selected views (APD.cu:2012-2052, :2160-2199).
 struct SweepCtx { float4 pl; float depth, weight_normal, kb, disp; int valid; };

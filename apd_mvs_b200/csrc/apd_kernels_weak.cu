@@ -363,40 +363,6 @@ __device__ float ncc_deform(const Args &a, const RefConst &rc, const ViewConst &
 	return (float)fma((double)center_cost, 0.25, (double)strong_cost * 0.75);
 }
 
-// geometric term, shared with the strong TU (defined there as a __device__ inline in the header would
-// duplicate code; it is small, so it is restated here from APD.cu:752-789 with the same operations)
-__device__ __forceinline__ float geom_cost_w(const Args &a, const RefConst &rc, const ViewConst &vc, int layer, const float4 pl, float xf, float yf) {
-	const float depth = plane_depth(rc, pl, xf, yf);
-	float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
-	const float *R = rc.cam.R;
-	float Px = rc.cam.c[0] + fmaf(R[6], depth, fmaf(R[0], X0, R[3] * X1));
-	float Py = rc.cam.c[1] + fmaf(R[7], depth, fmaf(R[1], X0, R[4] * X1));
-	float Pz = rc.cam.c[2] + fmaf(R[8], depth, fmaf(R[2], X0, R[5] * X1));
-	const apd_camera &s = vc.cam;
-	float tx = s.t[0] + fmaf(s.R[2], Pz, fmaf(s.R[0], Px, s.R[1] * Py));
-	float ty = s.t[1] + fmaf(s.R[5], Pz, fmaf(s.R[3], Px, s.R[4] * Py));
-	float tz = s.t[2] + fmaf(s.R[8], Pz, fmaf(s.R[6], Px, s.R[7] * Py));
-	float rd = rcpf(fmaf(s.K[8], tz, fmaf(s.K[6], tx, s.K[7] * ty)));
-	float sx = fmaf(s.K[2], tz, fmaf(s.K[0], tx, s.K[1] * ty)) * rd;
-	float sy = fmaf(s.K[5], tz, fmaf(s.K[3], tx, s.K[4] * ty)) * rd;
-	const float sd = tex2DLayered<float>(a.depth_tex, (float)(int)sx + 0.5f, (float)(int)sy + 0.5f, layer);
-	if (sd == 0.0f) return 3.0f;
-	const float rsK0 = rcpf(s.K[0]), rsK4 = rcpf(s.K[4]);
-	float Y0 = (sd * (sx - s.K[2])) * rsK0;
-	float Y1 = (sd * (sy - s.K[5])) * rsK4;
-	float Qx = s.c[0] + fmaf(s.R[6], sd, fmaf(s.R[0], Y0, s.R[3] * Y1));
-	float Qy = s.c[1] + fmaf(s.R[7], sd, fmaf(s.R[1], Y0, s.R[4] * Y1));
-	float Qz = s.c[2] + fmaf(s.R[8], sd, fmaf(s.R[2], Y0, s.R[5] * Y1));
-	const float *K = rc.cam.K; const float *t = rc.cam.t;
-	float ux = t[0] + fmaf(R[2], Qz, fmaf(R[0], Qx, R[1] * Qy));
-	float uy = t[1] + fmaf(R[5], Qz, fmaf(R[3], Qx, R[4] * Qy));
-	float uz = t[2] + fmaf(R[8], Qz, fmaf(R[6], Qx, R[7] * Qy));
-	float rb = rcpf(fmaf(K[8], uz, fmaf(K[6], ux, K[7] * uy)));
-	float dc = fmaf(-fmaf(K[2], uz, fmaf(K[0], ux, K[1] * uy)), rb, xf);
-	float dr = fmaf(-fmaf(K[5], uz, fmaf(K[3], ux, K[4] * uy)), rb, yf);
-	return fminf(sqrtaf(fmaf(dc, dc, dr * dr)), 3.0f);
-}
-
 // weighted cost of one plane for a WEAK pixel over the sampled views:
 //   sum_v w_v * (ncc_deform + geom_factor * geom) (APD.cu:918-927, 960-969, 1464-1471)
 __device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *sv, const float4 pl, const Anchors &an, const float *rcol,
@@ -411,7 +377,7 @@ __device__ float weak_cost(const Args &a, const RefConst &rc, const ViewConst *s
 		const int w = vw_get(vw, v);
 		if (w == 0) continue;
 		float c = ncc_deform(a, rc, sv[v], v, pl, an, rcol, px, py, inv36, inv9);
-		if (a.geom) c = fmaf(a.geom_factor, geom_cost_w(a, rc, sv[v], v + 1, pl, (float)px, (float)py), c);
+		if (a.geom) c = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, pl, (float)px, (float)py), c);
 		acc = fmaf((float)w, c, acc);
 		if (prune && acc * inv_wn >= limit) break;
 	}
@@ -534,7 +500,7 @@ __global__ void __launch_bounds__(kWeakNT, 3) k_weak(const Args a, const int ite
 				const int w = vw_get(vw, v);
 				if (w == 0) continue;
 				float c = CM(k, v);
-				if (a.geom) c = fl ? fmaf(a.geom_factor, geom_cost_w(a, rc, sv[v], v + 1, pl, xf, yf), c) : fmaf(a.geom_factor, 3.0f, c);
+				if (a.geom) c = fl ? fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, pl, xf, yf), c) : fmaf(a.geom_factor, 3.0f, c);
 				acc = fmaf((float)w, c, acc);
 			}
 			(void)miss;
@@ -620,22 +586,18 @@ __global__ void __launch_bounds__(kWeakNT, 3) k_weak(const Args a, const int ite
 }
 
 // ------------------------------------------------------------------------------------------------
-static int8_t *g_dummy = nullptr;
 cudaError_t launch_nearest_strong(cudaStream_t st, const Args &a) {
 	// row scratch: reuse the fit-plane buffer (16 B/px, rewritten by K8 before any use)
 	int8_t *rowdx = reinterpret_cast<int8_t *>(a.fit_planes);
 	dim3 b(32, 8), g((a.W + 31) / 32, (a.H + 7) / 8);
 	k_row_nearest<<<g, b, 0, st>>>(a.states, a.W, a.H, rowdx);
 	k_nearest_strong<<<g, b, 0, st>>>(a, rowdx);
-	(void)g_dummy;
 	return cudaGetLastError();
 }
-static AnchorConsts *g_ac[16] = {nullptr};
-cudaError_t launch_gen_anchors(cudaStream_t st, const Args &a) {
-	int dev = 0; cudaGetDevice(&dev);
-	if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
-	if (!g_ac[dev]) { cudaError_t e = cudaMalloc((void **)&g_ac[dev], 4 * sizeof(AnchorConsts)); if (e != cudaSuccess) return e; }
-	AnchorConsts *ac = g_ac[dev] + (a.rotate_time == 1 ? 0 : a.rotate_time == 2 ? 1 : 2);
+size_t anchor_consts_bytes() { return sizeof(AnchorConsts); }
+// `consts`: the handle's own AnchorConsts buffer (no process-global state: handles on one device may run concurrently)
+cudaError_t launch_gen_anchors(cudaStream_t st, const Args &a, void *consts) {
+	AnchorConsts *ac = static_cast<AnchorConsts *>(consts);
 	launch_anchor_consts(st, a.rotate_time, ac);
 	dim3 b(32, 4), g((a.W + 31) / 32, (a.H + 3) / 4);
 	k_gen_anchors<<<g, b, 0, st>>>(a, ac);

@@ -80,10 +80,13 @@ def _rects(rng: np.random.Generator, n: int, frac: float):
 
 @torch.no_grad()
 def make_scene(W: int, H: int, n_src: int, seed: int = MASTER_SEED, device: str = "cpu",
-               textureless: bool = True, n_waves: int = 24, chunk_rows: int = 512) -> dict:
+               textureless: bool = True, n_waves: int = 24, chunk_rows: int = 512, only=None, ref_index: int = 0) -> dict:
     """Returns images [N,H,W] float32 (0..255), cameras (CAMERA_DTYPE[N]), depth [N,H,W] float32
-    (exact per-view depth), normal [H,W,3] float32 (reference view, world frame), weak_mask [H,W]
-    bool (reference pixels on textureless rectangles)."""
+    (exact per-view depth), normal [H,W,3] float32 (view `ref_index`, world frame), weak_mask [H,W]
+    bool (pixels of view `ref_index` on textureless rectangles). `only`: render just these views (the
+    others stay zero) - a rank of the multi-GPU bench renders its own reference view's normal and mask
+    and receives the images and depth maps from rank 0. The +-0.5 noise on the rectangles depends on
+    the render order, so images are comparable only between calls with the same `only`."""
     rng = np.random.default_rng(seed)
     cams = make_cameras(W, H, n_src)
     kx, ky, phase, amp = _texture_params(rng, W, n_waves)
@@ -100,7 +103,9 @@ def make_scene(W: int, H: int, n_src: int, seed: int = MASTER_SEED, device: str 
     weak = torch.zeros((H, W), dtype=torch.bool, device=dev)
     noise_gen = torch.Generator(device="cpu").manual_seed(seed + 17)
     xs = torch.arange(W, dtype=dd, device=dev)
-    for i in range(N):
+    if only is not None:
+        images.zero_(); depth.zero_()
+    for i in (range(N) if only is None else only):
         K = cams[i]["K"].astype(np.float64)
         R = torch.tensor(cams[i]["R"].astype(np.float64).reshape(3, 3), device=dev)
         c = torch.tensor(cams[i]["c"].astype(np.float64), device=dev)
@@ -132,16 +137,16 @@ def make_scene(W: int, H: int, n_src: int, seed: int = MASTER_SEED, device: str 
                 inside = (X[..., 0] > xa) & (X[..., 0] < xb) & (X[..., 1] > ya) & (X[..., 1] < yb)
                 nz = (torch.rand((r1 - r0, W), generator=noise_gen, dtype=torch.float32) - 0.5).to(dev, dd)
                 val = torch.where(inside, level + nz, val)
-                if i == 0:
+                if i == ref_index:
                     weak[r0:r1] |= inside
             images[i, r0:r1] = val.to(torch.float32)
             depth[i, r0:r1] = best_t.to(torch.float32)        # camera-frame z of the hit (ray has z = 1)
-            if i == 0:
+            if i == ref_index:
                 n = torch.stack([planes[best_i, 1], planes[best_i, 2], -torch.ones_like(best_t)], dim=-1)
                 n = n / n.norm(dim=-1, keepdim=True)
                 normal[r0:r1] = n.to(torch.float32)
     return {"images": images, "cameras": cams, "depth": depth, "normal": normal, "weak_mask": weak,
-            "W": W, "H": H, "n_src": n_src}
+            "W": W, "H": H, "n_src": n_src, "ref_index": ref_index}
 
 
 def make_priors(scene: dict, seed: int = MASTER_SEED + 1, depth_noise: float = 0.01, normal_deg: float = 5.0,
@@ -160,7 +165,7 @@ def make_priors(scene: dict, seed: int = MASTER_SEED + 1, depth_noise: float = 0
     states = np.full((H, W), 1, dtype=np.uint8)
     states[scene["weak_mask"].cpu().numpy()] = 0
     states[:6, :] = 2; states[-6:, :] = 2; states[:, :6] = 2; states[:, -6:] = 2
-    n_src = scene["n_src"]
+    n_src = depth.shape[0] - 1
     views = np.full((H, W), views_mask & ((1 << n_src) - 1), dtype=np.uint32)
     src_depth = (depth * (1.0 + depth_noise * torch.randn(depth.shape, generator=g))).to(torch.float32).contiguous().numpy()
     return {"planes": planes, "states": states, "views": views, "depths": src_depth}
