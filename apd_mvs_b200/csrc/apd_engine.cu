@@ -179,6 +179,13 @@ extern "C" int apd_set_num_images(apd_handle h, int num_images) {
 	return APD_OK;
 }
 
+extern "C" int apd_reset_inputs(apd_handle h) {
+	if (!h) return APD_E_ARG;
+	h->have_images = h->have_cams = h->have_depths = h->have_planes = h->have_states = false;
+	return APD_OK;
+}
+extern "C" int apd_get_capacity(apd_handle h) { return h ? h->capacity : 0; }
+
 extern "C" int apd_set_cameras(apd_handle h, const apd_camera *cams) {
 	if (!h || !cams) return APD_E_ARG;
 	CKH(cudaSetDevice(h->device));
@@ -329,7 +336,7 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 #define STAGE_END() do { CKH(cudaGetLastError()); CKH(cudaEventRecord(h->events[stage + 1], st)); if (stage == stage_end) goto done; ++stage; } while (0)
 	launch_rng_seed(st, a, h->seed); h->launches++; STAGE_END();                                          // 0  K1
 	if (apd_on) { CKH(launch_nearest_strong(st, a)); h->launches += 2; } STAGE_END();                         // 1  K2
-	if (apd_on) { CKH(launch_gen_anchors(st, a, h->anchor_consts)); h->launches += 2; } STAGE_END();        // 2  K3
+	if (apd_on) { CKH(launch_gen_anchors(st, a, h->anchor_consts)); h->launches += 3; } STAGE_END();        // 2  K3
 	if (apd_on) {                                                                                          // 3  K4 (+ the WEAK lists K9/K10 walk)
 		CKH(launch_demote_unreliable(st, a)); h->launches++;
 		if (h->weak_impl == 1) { CKH(launch_weak_lists(st, a, true)); h->launches++; }

@@ -178,6 +178,103 @@ __global__ void k_planes_to_normals(const float4 *planes, float *normals, size_t
 }
 __global__ void k_fill_int(int *a, int v, size_t n) { const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (p < n) a[p] = v; }
 
+
+// ---- Tanks-and-Temples variants: RunFusion_TAT_Intermediate (APD.cpp:979-1147) and RunFusion_TAT_advanced (:1149-1296) ----------
+// These loops have a different sequential dependency than the ETH variant. Accepted pixels mark only THEIR OWN view's mask
+// (masks[ref], :1139 / :1288), which is read when that view is a SOURCE of a later problem - so inside one view all pixels
+// see the same marks. But the per-source measurements live in ONE `std::vector<CostData> diff` per view that is NOT reset
+// between pixels (:1059 / :1230): when a pixel's projection falls outside the source image, onto a marked pixel or onto
+// an invalid depth, diff[j] keeps the values of the LAST EARLIER pixel (raster order) that did measure source j - including
+// its source coordinates, which the Intermediate variant uses for the colour (:1123-1128). Kept exactly: k_tat_measure writes,
+// per source j, the pixel's own index where it measured and -1 elsewhere; an inclusive max-scan over the raster order turns
+// that into "index of the last measuring pixel <= p"; k_tat_decide reads the measurements from there.
+struct TatArgs {
+	int W, H, n_src, variant;            // variant 1 = Intermediate, 2 = advanced
+	FView ref; FCam ref_cam;
+	const FView *src; const FCam *src_cam;
+	int *last;                           // [n_src][W*H] own index where source j was measured / after the scan: last measuring pixel
+	int *srcq;                           // [n_src][W*H] source pixel of the measurement
+	float *dist, *depth, *angle;         // [n_src][W*H]
+	uint8_t *status; float3 *pt_xyz, *pt_col;
+};
+__global__ void k_tat_measure(const TatArgs a) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+	if (c >= a.W || r >= a.H) return;
+	const size_t n = (size_t)a.W * a.H; const size_t p = (size_t)r * a.W + c;
+	bool processed = !(a.ref.block && a.ref.block[p] < 128);
+	const float ref_depth = a.ref.depth[p];
+	if (ref_depth <= 0.0) processed = false;
+	a.status[p] = processed ? kUndecided : kRejected;
+	float3 X = make_float3(0.f, 0.f, 0.f);
+	if (processed) X = point_on_world(c, r, ref_depth, a.ref_cam);
+	const float *ref_normal = a.ref.normal + 3 * p;
+	for (int j = 0; j < a.n_src; ++j) {
+		int last = -1;
+		if (processed) {
+			const FView &sv = a.src[j]; const FCam &sc = a.src_cam[j];
+			float2 pt; float proj_depth;
+			project_camera(X, sc, pt, proj_depth);
+			const int src_r = int(pt.y + 0.5f), src_c = int(pt.x + 0.5f);
+			if (src_c >= 0 && src_c < a.W && src_r >= 0 && src_r < a.H) {
+				const size_t q = (size_t)src_r * a.W + src_c;
+				const float src_depth = sv.depth[q];
+				if (sv.mask[q] != 1 && !(src_depth <= 0.0)) {
+					const float3 tX = point_on_world(src_c, src_r, src_depth, sc);
+					float2 tpt;
+					project_camera(tX, a.ref_cam, tpt, proj_depth);
+					const double ex = (double)(c - tpt.x), ey = (double)(r - tpt.y);
+					a.dist[(size_t)j * n + p] = (float)sqrt(ex * ex + ey * ey);
+					a.depth[(size_t)j * n + p] = fabsf(proj_depth - ref_depth) / ref_depth;
+					a.angle[(size_t)j * n + p] = get_angle(ref_normal, sv.normal + 3 * q);
+					a.srcq[(size_t)j * n + p] = (int)q;
+					last = (int)p;
+				}
+			}
+		}
+		a.last[(size_t)j * n + p] = last;
+	}
+}
+__global__ void k_tat_decide(const TatArgs a) {
+	const size_t n = (size_t)a.W * a.H;
+	const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n || a.status[p] != kUndecided) return;
+	const float dist_base = 0.25f;
+	const float depth_base = (a.variant == 1) ? 1.0f / 3500.0f : 1.0f / 3000.0f;
+	const float angle_base = 0.06981317007977318f, angle_grad = 0.05235987755982988f;
+	uint8_t st = kRejected;
+	for (int k = 2; k <= a.n_src; ++k) {
+		int count = 0; unsigned use = 0u;
+		for (int j = 0; j < a.n_src; ++j) {
+			const int q = a.last[(size_t)j * n + p];
+			if (q < 0) continue;                                   // never measured so far: CostData() = FLT_MAX
+			const size_t o = (size_t)j * n + q;
+			bool ok = a.dist[o] < k * dist_base && a.depth[o] < k * depth_base;
+			if (a.variant == 1) ok = ok && a.angle[o] < (k * angle_grad + angle_base);
+			if (ok) { count++; use |= 1u << j; }
+		}
+		if (count >= k) {
+			const int c = (int)(p % a.W), r = (int)(p / a.W);
+			const uchar3 rc = a.ref.bgr[p];
+			float col[3] = {(float)rc.x, (float)rc.y, (float)rc.z};
+			if (a.variant == 1) {
+				for (int j = 0; j < a.n_src; ++j) {
+					if (!((use >> j) & 1u)) continue;
+					const uchar3 sc = a.src[j].bgr[a.srcq[(size_t)j * n + a.last[(size_t)j * n + p]]];
+					col[0] += (float)sc.x; col[1] += (float)sc.y; col[2] += (float)sc.z;
+				}
+				col[0] /= (count + 1.0f); col[1] /= (count + 1.0f); col[2] /= (count + 1.0f);
+			}
+			a.pt_xyz[p] = point_on_world(c, r, a.ref.depth[p], a.ref_cam);
+			a.pt_col[p] = make_float3(col[0], col[1], col[2]);
+			a.ref.mask[p] = 1;
+			st = kAccepted;
+			break;
+		}
+	}
+	a.status[p] = st;
+}
+struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
+
 struct HostView { uchar3 *bgr = nullptr; float *depth = nullptr, *normal = nullptr; uint8_t *states = nullptr, *block = nullptr, *mask = nullptr; int *claim = nullptr; bool set = false, has_block = false; FCam cam; };
 struct HostProblem { int ref; std::vector<int> srcs; };
 
@@ -189,6 +286,9 @@ struct apd_fusion {
 	std::vector<HostView> views;
 	std::vector<HostProblem> problems;
 	FView *d_src = nullptr; FCam *d_src_cam = nullptr;
+	size_t cand_src = 0;       // source views the cand/term buffers were allocated for
+	size_t tat_src = 0; int *tat_srcq = nullptr; float *tat_depth = nullptr, *tat_angle = nullptr;     // T&T variants: extra per-(source, pixel) arrays
+	void *tat_tmp = nullptr; size_t tat_tmp_bytes = 0;
 	int *cand = nullptr; float *term = nullptr; uint8_t *status = nullptr; float3 *pt_xyz = nullptr, *pt_col = nullptr;
 	int *undecided = nullptr, *flags = nullptr, *offs = nullptr; void *cub_tmp = nullptr; size_t cub_bytes = 0;
 	float4 *tmp_planes = nullptr;
@@ -231,7 +331,7 @@ extern "C" void apd_fusion_destroy(apd_fusion_handle f) {
 	cudaSetDevice(f->device);
 	if (f->stream) cudaStreamSynchronize(f->stream);
 	for (auto &v : f->views) { void *p[] = {v.bgr, v.depth, v.normal, v.states, v.block, v.mask, v.claim}; for (void *q : p) if (q) cudaFree(q); }
-	void *p[] = {f->d_src, f->d_src_cam, f->cand, f->term, f->status, f->pt_xyz, f->pt_col, f->undecided, f->flags, f->offs, f->cub_tmp, f->tmp_planes, f->out_xyz, f->out_col};
+	void *p[] = {f->d_src, f->d_src_cam, f->cand, f->term, f->status, f->pt_xyz, f->pt_col, f->undecided, f->flags, f->offs, f->cub_tmp, f->tmp_planes, f->out_xyz, f->out_col, f->tat_srcq, f->tat_depth, f->tat_angle, f->tat_tmp};
 	for (void *q : p) if (q) cudaFree(q);
 	if (f->stream) cudaStreamDestroy(f->stream);
 	delete f;
@@ -283,6 +383,47 @@ extern "C" int apd_fusion_add_problem(apd_fusion_handle f, int ref_view, const i
 	return APD_OK;
 }
 
+// raster-order compaction of the accepted points of the view just decided (f->status), appended to the cloud
+static int append_accepted(apd_fusion_handle f) {
+	const size_t n = (size_t)f->W * f->H;
+	cudaStream_t st = f->stream;
+	const unsigned g1 = (unsigned)((n + 255) / 256);
+	k_fuse_flags<<<g1, 256, 0, st>>>(f->status, f->flags, n);
+	cub::DeviceScan::ExclusiveSum(f->cub_tmp, f->cub_bytes, f->flags, f->offs, (int)n, st);
+	int last_off = 0, last_flag = 0;
+	CKF(cudaMemcpyAsync(&last_off, f->offs + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+	CKF(cudaMemcpyAsync(&last_flag, f->flags + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+	CKF(cudaStreamSynchronize(st));
+	const size_t cnt = (size_t)last_off + last_flag;
+	if (f->out_n + cnt > f->out_cap) {
+		size_t cap = f->out_cap ? f->out_cap : n;
+		while (cap < f->out_n + cnt) cap *= 2;
+		float3 *nx = nullptr, *nc = nullptr;
+		CKF(cudaMalloc((void **)&nx, cap * 12)); CKF(cudaMalloc((void **)&nc, cap * 12));
+		if (f->out_n) { CKF(cudaMemcpyAsync(nx, f->out_xyz, f->out_n * 12, cudaMemcpyDeviceToDevice, st)); CKF(cudaMemcpyAsync(nc, f->out_col, f->out_n * 12, cudaMemcpyDeviceToDevice, st)); }
+		CKF(cudaStreamSynchronize(st));
+		if (f->out_xyz) cudaFree(f->out_xyz);
+		if (f->out_col) cudaFree(f->out_col);
+		f->out_xyz = nx; f->out_col = nc; f->out_cap = cap;
+	}
+	if (cnt) k_fuse_compact<<<g1, 256, 0, st>>>(f->status, f->offs, f->pt_xyz, f->pt_col, f->out_xyz + f->out_n, f->out_col + f->out_n, n);
+	f->out_n += cnt;
+	CKF(cudaGetLastError());
+	return APD_OK;
+}
+
+static int ensure_pair_buffers(apd_fusion_handle f, size_t max_src) {
+	const size_t n = (size_t)f->W * f->H;
+	if (max_src > f->cand_src) {       // problems may be added between runs: grow with the largest source count seen
+		if (f->cand) { cudaFree(f->cand); f->cand = nullptr; }
+		if (f->term) { cudaFree(f->term); f->term = nullptr; }
+		f->cand_src = 0;
+		CKF(cudaMalloc((void **)&f->cand, max_src * n * 4)); CKF(cudaMalloc((void **)&f->term, max_src * n * 4));
+		f->cand_src = max_src;
+	}
+	return APD_OK;
+}
+
 extern "C" int apd_fusion_run(apd_fusion_handle f) {
 	if (!f) return APD_E_ARG;
 	for (auto &v : f->views) if (!v.set) return ffail(f, APD_E_STATE, "every view needs apd_fusion_set_view first");
@@ -290,7 +431,7 @@ extern "C" int apd_fusion_run(apd_fusion_handle f) {
 	const size_t n = (size_t)f->W * f->H;
 	size_t max_src = 1;
 	for (auto &p : f->problems) if (p.srcs.size() > max_src) max_src = p.srcs.size();
-	if (!f->cand) { CKF(cudaMalloc((void **)&f->cand, max_src * n * 4)); CKF(cudaMalloc((void **)&f->term, max_src * n * 4)); }
+	{ int rc = ensure_pair_buffers(f, max_src); if (rc != APD_OK) return rc; }
 	cudaStream_t st = f->stream;
 	cudaEvent_t e0, e1; CKF(cudaEventCreate(&e0)); CKF(cudaEventCreate(&e1));
 	CKF(cudaEventRecord(e0, st));
@@ -329,27 +470,61 @@ extern "C" int apd_fusion_run(apd_fusion_handle f) {
 		// the pixels k_fuse_decide resolved in the last round still hold claims: clear them for the next view
 		for (int s : pb.srcs) k_fill_int<<<g1, 256, 0, st>>>(f->views[s].claim, INT_MAX, n);
 		if (rounds > f->max_rounds) f->max_rounds = rounds;
-		// raster-order compaction of the accepted points, appended to the cloud
-		k_fuse_flags<<<g1, 256, 0, st>>>(f->status, f->flags, n);
-		cub::DeviceScan::ExclusiveSum(f->cub_tmp, f->cub_bytes, f->flags, f->offs, (int)n, st);
-		int last_off = 0, last_flag = 0;
-		CKF(cudaMemcpyAsync(&last_off, f->offs + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-		CKF(cudaMemcpyAsync(&last_flag, f->flags + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-		CKF(cudaStreamSynchronize(st));
-		const size_t cnt = (size_t)last_off + last_flag;
-		if (f->out_n + cnt > f->out_cap) {
-			size_t cap = f->out_cap ? f->out_cap : n;
-			while (cap < f->out_n + cnt) cap *= 2;
-			float3 *nx = nullptr, *nc = nullptr;
-			CKF(cudaMalloc((void **)&nx, cap * 12)); CKF(cudaMalloc((void **)&nc, cap * 12));
-			if (f->out_n) { CKF(cudaMemcpyAsync(nx, f->out_xyz, f->out_n * 12, cudaMemcpyDeviceToDevice, st)); CKF(cudaMemcpyAsync(nc, f->out_col, f->out_n * 12, cudaMemcpyDeviceToDevice, st)); }
-			CKF(cudaStreamSynchronize(st));
-			if (f->out_xyz) cudaFree(f->out_xyz); if (f->out_col) cudaFree(f->out_col);
-			f->out_xyz = nx; f->out_col = nc; f->out_cap = cap;
+		{ int rc = append_accepted(f); if (rc != APD_OK) return rc; }
+	}
+	CKF(cudaEventRecord(e1, st));
+	CKF(cudaStreamSynchronize(st));
+	float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); f->gpu_ms = ms;
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	return APD_OK;
+}
+
+extern "C" int apd_fusion_run_tat(apd_fusion_handle f, int variant) {
+	if (!f) return APD_E_ARG;
+	if (variant != APD_FUSION_TAT_INTERMEDIATE && variant != APD_FUSION_TAT_ADVANCED) return ffail(f, APD_E_ARG, "variant must be APD_FUSION_TAT_INTERMEDIATE or APD_FUSION_TAT_ADVANCED");
+	for (auto &v : f->views) if (!v.set) return ffail(f, APD_E_STATE, "every view needs apd_fusion_set_view first");
+	CKF(cudaSetDevice(f->device));
+	const size_t n = (size_t)f->W * f->H;
+	size_t max_src = 1;
+	for (auto &p : f->problems) if (p.srcs.size() > max_src) max_src = p.srcs.size();
+	{ int rc = ensure_pair_buffers(f, max_src); if (rc != APD_OK) return rc; }
+	if (max_src > f->tat_src) {
+		for (void *q : {(void *)f->tat_srcq, (void *)f->tat_depth, (void *)f->tat_angle}) if (q) cudaFree(q);
+		f->tat_srcq = nullptr; f->tat_depth = f->tat_angle = nullptr; f->tat_src = 0;
+		CKF(cudaMalloc((void **)&f->tat_srcq, max_src * n * 4)); CKF(cudaMalloc((void **)&f->tat_depth, max_src * n * 4)); CKF(cudaMalloc((void **)&f->tat_angle, max_src * n * 4));
+		f->tat_src = max_src;
+	}
+	cudaStream_t st = f->stream;
+	if (!f->tat_tmp) {
+		cub::DeviceScan::InclusiveScan(nullptr, f->tat_tmp_bytes, f->cand, f->cand, MaxOp(), (int)n, st);
+		CKF(cudaMalloc(&f->tat_tmp, f->tat_tmp_bytes ? f->tat_tmp_bytes : 16));
+	}
+	cudaEvent_t e0, e1; CKF(cudaEventCreate(&e0)); CKF(cudaEventCreate(&e1));
+	CKF(cudaEventRecord(e0, st));
+	const unsigned g1 = (unsigned)((n + 255) / 256);
+	for (auto &v : f->views) CKF(cudaMemsetAsync(v.mask, 0, n, st));
+	f->out_n = 0; f->max_rounds = 1;
+	for (const HostProblem &pb : f->problems) {
+		TatArgs a; memset(&a, 0, sizeof(a));
+		a.W = f->W; a.H = f->H; a.n_src = (int)pb.srcs.size(); a.variant = variant;
+		auto fv = [&](const HostView &v) { FView o; o.bgr = v.bgr; o.depth = v.depth; o.normal = v.normal; o.states = v.states; o.block = v.has_block ? v.block : nullptr; o.mask = v.mask; o.claim = v.claim; return o; };
+		a.ref = fv(f->views[pb.ref]); a.ref_cam = f->views[pb.ref].cam;
+		std::vector<FView> sv; std::vector<FCam> sc;
+		for (int s : pb.srcs) { sv.push_back(fv(f->views[s])); sc.push_back(f->views[s].cam); }
+		if (a.n_src) {
+			CKF(cudaMemcpyAsync(f->d_src, sv.data(), sizeof(FView) * sv.size(), cudaMemcpyHostToDevice, st));
+			CKF(cudaMemcpyAsync(f->d_src_cam, sc.data(), sizeof(FCam) * sc.size(), cudaMemcpyHostToDevice, st));
+			CKF(cudaStreamSynchronize(st));          // sv / sc are locals
 		}
-		if (cnt) k_fuse_compact<<<g1, 256, 0, st>>>(f->status, f->offs, f->pt_xyz, f->pt_col, f->out_xyz + f->out_n, f->out_col + f->out_n, n);
-		f->out_n += cnt;
+		a.src = f->d_src; a.src_cam = f->d_src_cam; a.last = f->cand; a.srcq = f->tat_srcq; a.dist = f->term; a.depth = f->tat_depth; a.angle = f->tat_angle;
+		a.status = f->status; a.pt_xyz = f->pt_xyz; a.pt_col = f->pt_col;
+		const dim3 b2(32, 8), g2((f->W + 31) / 32, (f->H + 7) / 8);
+		k_tat_measure<<<g2, b2, 0, st>>>(a);
+		for (int j = 0; j < a.n_src; ++j)          // "last earlier pixel that measured source j", in raster order
+			cub::DeviceScan::InclusiveScan(f->tat_tmp, f->tat_tmp_bytes, a.last + (size_t)j * n, a.last + (size_t)j * n, MaxOp(), (int)n, st);
+		k_tat_decide<<<g1, 256, 0, st>>>(a);
 		CKF(cudaGetLastError());
+		{ int rc = append_accepted(f); if (rc != APD_OK) return rc; }
 	}
 	CKF(cudaEventRecord(e1, st));
 	CKF(cudaStreamSynchronize(st));

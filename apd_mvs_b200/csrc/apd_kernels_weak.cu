@@ -7,6 +7,8 @@
 //                                          -> :892-980, deformable NCC :400-528
 // Numerics follow the same contract as apd_device.cuh (explicit FMAs where the reference SASS has them).
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include "apd_device.cuh"
 
 namespace apd {
@@ -94,15 +96,24 @@ __device__ __forceinline__ float plane_dist(const float4 pl, const float3 p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3. One thread per WEAK pixel: deformable-anchor search along 8 base directions x rotate_time
-// sub-rotations, then a 50-iteration RANSAC plane through the anchors' 3-D points.
+// K3. One thread per WEAK pixel of the compacted list (k_weak_lists<false>): deformable-anchor search along 8 base
+// directions x rotate_time sub-rotations, then a 50-iteration RANSAC plane through the anchors' 3-D points.
+// RANGE = the jitter range `shift_range` (APD.cu:1795-1796: 8 / 3 / 1 for rotate_time 1 / 2 / 4) as a compile-time
+// constant, 0 = read it at run time. The kernel is ALU bound (ncu: 76 % of the ALU pipe, profiles/r02_*), so:
+//  * `% shift_range` becomes a multiply-shift;
+//  * with RANGE == 1 the jitter is always 0, the four tries of a radius test the SAME candidate against read-only
+//    data, so it is tested once; the generator still advances by the 4 (success at the first try) or 16 draws the
+//    reference consumes.
+__device__ __forceinline__ void rng_skip(Rng &r, int n) { for (int i = 0; i < n; ++i) (void)rng_next(r); }
+
+template <int RANGE>
 __global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorConsts *acp) {
-	const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
-	if (px >= a.W || py >= a.H) return;
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= a.wctrl[2]) return;
 	const int W = a.W, H = a.H;
 	const size_t n = (size_t)W * H;
-	const int center = py * W + px;
-	if (a.states[center] != APD_WEAK) return;
+	const int center = a.wlist[idx];
+	const int py = center / W, px = center - py * W;
 	const AnchorConsts ac = *acp;
 	const RefConst rc = *a.ref;
 	for (int k = 0; k < APD_NEIGHBOUR_NUM; ++k) a.anchors[(size_t)k * n + center] = make_short2(-1, -1);
@@ -111,11 +122,16 @@ __global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorC
 	short2 sp[32]; unsigned valid = 0u; int found = 0;
 	for (int i = 0; i < 32; ++i) sp[i] = make_short2(-1, -1);
 	const float pxf = (float)px, pyf = (float)py, Wf = (float)W, Hf = (float)H;
-	const unsigned range = (unsigned)ac.shift_range;
+	const unsigned range = RANGE ? (unsigned)RANGE : (unsigned)ac.shift_range;
+	// A run-time +0.0f the compiler cannot prove to be zero. When the two loops below are unrolled, normalize2() of the
+	// constant base directions would be folded at BUILD time - and a folded rsqrt.approx is the correctly rounded value,
+	// whereas the MUFU.RSQ the reference executes is not (1 ulp apart for (+-1, +-1)): 227 of 9.75 M WEAK pixels of the
+	// 6221x4146 case then take a different branch somewhere along their search (found with the full-size parity check).
+	const float rt_zero = ac.thresh * 0.0f;
 	int base = -1;
 	for (int ox = -1; ox <= 1; ++ox) for (int oy = -1; oy <= 1; ++oy) {
 		if (ox == 0 && oy == 0) continue;
-		float dx = (float)ox, dy = (float)oy;
+		float dx = (float)ox + rt_zero, dy = (float)oy + rt_zero;
 		normalize2(dx, dy);
 		++base;
 		for (int rot = 0; rot < a.rotate_time; ++rot) {
@@ -124,25 +140,36 @@ __global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorC
 				const float rf = (float)radius;
 				const float tx = fmaf(rf, dx, pxf), ty = fmaf(rf, dy, pyf);
 				if (tx < 0.0f || ty < 0.0f || tx >= Wf || ty >= Hf) break;
-				for (int t = 0; t < 4; ++t) {
+				const int tries = (RANGE == 1) ? 1 : 4;
+				for (int t = 0; t < tries; ++t) {
 					// (curand()%2==0 ? 1 : -1) * curand() % shift_range, all in unsigned arithmetic (APD.cu:1813-1814)
-					const uint32_t d1 = rng_next(rng), d2 = rng_next(rng), d3 = rng_next(rng), d4 = rng_next(rng);
-					const uint32_t xs = (((d1 & 1u) == 0u) ? d2 : (0u - d2)) % range;
-					const uint32_t ys = (((d3 & 1u) == 0u) ? d4 : (0u - d4)) % range;
+					uint32_t xs = 0u, ys = 0u;
+					if (RANGE != 1) {
+						const uint32_t d1 = rng_next(rng), d2 = rng_next(rng), d3 = rng_next(rng), d4 = rng_next(rng);
+						xs = (((d1 & 1u) == 0u) ? d2 : (0u - d2)) % range;
+						ys = (((d3 & 1u) == 0u) ? d4 : (0u - d4)) % range;
+					}
+					bool hit = false;
 					float ddx = fmaf(dx, 20.0f, (float)xs), ddy = fmaf(dy, 20.0f, (float)ys);
 					normalize2(ddx, ddy);
 					int nx = (short)(int)fmaf(rf, ddx, pxf), ny = (short)(int)fmaf(rf, ddy, pyf);
-					if (nx < 6 || ny < 6 || nx >= W - 6 || ny >= H - 6) continue;
-					int nc = nx + ny * W;
-					if (a.states[nc] != APD_STRONG) {
-						const short2 s = a.nearest[nc];
-						if (s.x == -1 || s.y == -1) continue;
-						nx = s.x; ny = s.y;
+					if (!(nx < 6 || ny < 6 || nx >= W - 6 || ny >= H - 6)) {
+						int nc = nx + ny * W;
+						bool ok = true;
+						if (a.states[nc] != APD_STRONG) {
+							const short2 s = a.nearest[nc];
+							if (s.x == -1 || s.y == -1) ok = false;
+							nx = s.x; ny = s.y;
+						}
+						if (ok) {
+							float tdx = (float)(nx - px), tdy = (float)(ny - py);
+							normalize2(tdx, tdy);
+							const float cosv = fmaf(tdx, dx, tdy * dy);
+							hit = cosv > ac.thresh;
+						}
 					}
-					float tdx = (float)(nx - px), tdy = (float)(ny - py);
-					normalize2(tdx, tdy);
-					const float cosv = fmaf(tdx, dx, tdy * dy);
-					if (cosv > ac.thresh) { sp[di] = make_short2((short)nx, (short)ny); valid |= 1u << di; ++found; break; }
+					if (RANGE == 1) rng_skip(rng, hit ? 4 : 16);     // first try succeeds, or all four fail alike
+					if (hit) { sp[di] = make_short2((short)nx, (short)ny); valid |= 1u << di; ++found; break; }
 				}
 				if ((valid >> di) & 1u) break;
 			}
@@ -596,11 +623,24 @@ cudaError_t launch_nearest_strong(cudaStream_t st, const Args &a) {
 }
 size_t anchor_consts_bytes() { return sizeof(AnchorConsts); }
 // `consts`: the handle's own AnchorConsts buffer (no process-global state: handles on one device may run concurrently)
+cudaError_t launch_weak_lists(cudaStream_t st, const Args &a, bool split);       // apd_kernels_weakq.cu
 cudaError_t launch_gen_anchors(cudaStream_t st, const Args &a, void *consts) {
 	AnchorConsts *ac = static_cast<AnchorConsts *>(consts);
 	launch_anchor_consts(st, a.rotate_time, ac);
-	dim3 b(32, 4), g((a.W + 31) / 32, (a.H + 3) / 4);
-	k_gen_anchors<<<g, b, 0, st>>>(a, ac);
+	// the list of all WEAK pixels (K3 is a full launch in the reference, APD.cu:2415); the grid covers the worst case,
+	// threads beyond the list's length leave at once
+	cudaError_t e = launch_weak_lists(st, a, false);
+	if (e != cudaSuccess) return e;
+	const size_t n = (size_t)a.W * a.H;
+	const unsigned g = (unsigned)((n + 127) / 128);
+	// shift_range = max((int)(tan(angle / 2) * 20), 1) with angle = 45 deg / rotate_time (APD.cu:1790-1796): 8, 3, 2, 1
+	// APD_K3_GENERIC=1: run-time jitter range and four tries per radius whatever rotate_time is (diagnostic)
+	static const bool generic = getenv("APD_K3_GENERIC") != nullptr;
+	if (generic) k_gen_anchors<0><<<g, 128, 0, st>>>(a, ac);
+	else if (a.rotate_time == 4) k_gen_anchors<1><<<g, 128, 0, st>>>(a, ac);
+	else if (a.rotate_time == 2) k_gen_anchors<3><<<g, 128, 0, st>>>(a, ac);
+	else if (a.rotate_time == 1) k_gen_anchors<8><<<g, 128, 0, st>>>(a, ac);
+	else k_gen_anchors<0><<<g, 128, 0, st>>>(a, ac);
 	return cudaGetLastError();
 }
 cudaError_t launch_demote_unreliable(cudaStream_t st, const Args &a) {

@@ -40,12 +40,39 @@ __host__ __device__ constexpr int wq_warp_words(int S) { return (kRefRows + 9 * 
 
 // ------------------------------------------------------------------------------------------------
 // Compacted WEAK lists. One warp owns an 8x8 pixel area, ordered as four 4x4 sub-areas so that eight consecutive list
-// entries (= the eight pixels a k_weak_q warp processes together) are a compact cluster. SPLIT: one list per colour,
-// restricted to the rows the reference's half launch reaches; otherwise one list of all WEAK pixels (K3 is a full launch).
+// entries (= the eight pixels a k_weak_q warp processes together) are a compact cluster; a block owns a 32x8 tile.
+// Blocks are numbered super-tile by super-tile (256x256 pixels = 8x32 tiles), not in raster order: the list comes out in
+// (roughly) that order, so the ~1800 warps of k_weak_q that work on neighbouring list entries at the same time fetch
+// their far-away anchor windows from a few hundred pixels around one place instead of from a band across the whole image.
+// (Measured at 6221x4146, nine source images = 0.9 GB against 126 MB of L2: no effect on k_weak_q, 124 vs 126 ms - its
+// full-resolution penalty of 1.3x per pixel against 1555x1036 is not an L2-locality problem; kept because it is free.)
+// SPLIT: one list per colour, restricted to the rows the reference's half launch reaches; otherwise one list of all
+// WEAK pixels (K3 is a full launch). The order of the entries does not affect any result.
+constexpr int kSuperX = 8, kSuperY = 32;      // tiles per super-tile
 template <bool SPLIT>
-__global__ void __launch_bounds__(128) k_weak_lists(const Args a) {
+__global__ void __launch_bounds__(128) k_weak_lists(const Args a, int tiles_x, int tiles_y, int supers_x) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int ax = blockIdx.x * 32 + warp * 8, ay = blockIdx.y * 8;
+	const int st = blockIdx.x / (kSuperX * kSuperY), within = blockIdx.x % (kSuperX * kSuperY);
+	const int tx = (st % supers_x) * kSuperX + within % kSuperX, ty = (st / supers_x) * kSuperY + within / kSuperX;
+	if (tx >= tiles_x || ty >= tiles_y) return;
+	if (!SPLIT) {
+		// K3's list: a warp takes two rows of 32 pixels of the tile, so 32 consecutive entries are (mostly) neighbours in a
+		// row - its threads walk rays through `states` / `nearest`, which are row-major byte / short2 maps
+#pragma unroll
+		for (int c = 0; c < 2; ++c) {
+			const int x = tx * 32 + lane, y = ty * 8 + warp * 2 + c;
+			bool weak = x < a.W && y < a.H;
+			if (weak) weak = a.states[(size_t)y * a.W + x] == APD_WEAK;
+			const unsigned b = __ballot_sync(0xffffffffu, weak);
+			if (b == 0u) continue;
+			int base = 0;
+			if (lane == 0) base = atomicAdd(&a.wctrl[2], __popc(b));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (weak) a.wlist[base + __popc(b & ((1u << lane) - 1u))] = y * a.W + x;
+		}
+		return;
+	}
+	const int ax = tx * 32 + warp * 8, ay = ty * 8;
 	const int sub = lane >> 3, j = lane & 7;
 	const int y = ay + (sub >> 1) * 4 + (j >> 1);
 	const int xb = ax + (sub & 1) * 4 + (j & 1) * 2;
@@ -53,14 +80,14 @@ __global__ void __launch_bounds__(128) k_weak_lists(const Args a) {
 #pragma unroll
 	for (int c = 0; c < 2; ++c) {
 		const int x = xb + (c ^ odd);                     // colour c: (x + y + c) even
-		bool weak = x < a.W && y < a.H && (!SPLIT || y < a.half_rows);
+		bool weak = x < a.W && y < a.H && y < a.half_rows;
 		if (weak) weak = a.states[(size_t)y * a.W + x] == APD_WEAK;
 		const unsigned b = __ballot_sync(0xffffffffu, weak);
 		if (b == 0u) continue;
 		int base = 0;
-		if (lane == 0) base = atomicAdd(&a.wctrl[SPLIT ? c : 2], __popc(b));
+		if (lane == 0) base = atomicAdd(&a.wctrl[c], __popc(b));
 		base = __shfl_sync(0xffffffffu, base, 0);
-		if (weak) a.wlist[(SPLIT ? c * a.wlist_stride : 0) + base + __popc(b & ((1u << lane) - 1u))] = y * a.W + x;
+		if (weak) a.wlist[c * a.wlist_stride + base + __popc(b & ((1u << lane) - 1u))] = y * a.W + x;
 	}
 }
 
@@ -87,35 +114,94 @@ __device__ __forceinline__ void wq_cache_window(const Args &a, int cx, int cy, f
 	sums[0] = R; sums[kWqPix] = RR;
 }
 
-// NCC of one window for up to NR planes of this lane at once (same reference taps; APD.cu:456-505 / :556-610)
-template <int INC, int NR>
-__device__ __forceinline__ void wq_window(cudaTextureObject_t tex, int layer, const float *h0, const float *h1, bool w0, bool w1,
-                                          int cx, int cy, float inv_w, const float *col, float sum_r, float sum_rr, float &o0, float &o1) {
-	NccSums t0 = {sum_r, sum_rr, 0.f, 0.f, 0.f}, t1 = t0;
+// ---- two evaluations per lane ("slots" 0 and 1), computed as packed fp32 pairs ---------------------------------------
+// A lane always carries two evaluations through the deformable NCC: two candidate planes against one view (cost matrix),
+// one plane against two views (current / fit / refinement hypotheses). Both slots execute the same operations on
+// different data, so every FMUL/FADD/FFMA of the evaluation is issued ONCE as an f32x2 instruction (lo = slot 0,
+// hi = slot 1; same IEEE roundings as the scalar forms, apd_device.cuh), which halves the issue slots of a kernel that ncu
+// showed to be issue bound once its fetches were compact (profiles/r02w_*).
+struct Homog2 { f32x2 h[9]; };
+
+// make_homography (apd_device.cuh) for both slots. Negations are moved onto an operand: -(a*b) == (-a)*b exactly.
+__device__ __forceinline__ Homog2 make_homography2(const RefConst &rc, const ViewConst &v0, const ViewConst &v1, const float4 p0, const float4 p1) {
+	const f32x2 RW = pk2(rcpf(p0.w), rcpf(p1.w));
+	const f32x2 NX = pk2(-p0.x, -p1.x), NY = pk2(-p0.y, -p1.y), NZ = pk2(-p0.z, -p1.z);
+	f32x2 H[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		const f32x2 t = pk2(v0.trel[r], v1.trel[r]);
+		H[3 * r + 0] = fma2(mul2(NX, t), RW, pk2(v0.Rrel[3 * r + 0], v1.Rrel[3 * r + 0]));
+		H[3 * r + 1] = fma2(mul2(NY, t), RW, pk2(v0.Rrel[3 * r + 1], v1.Rrel[3 * r + 1]));
+		H[3 * r + 2] = fma2(mul2(NZ, t), RW, pk2(v0.Rrel[3 * r + 2], v1.Rrel[3 * r + 2]));
+	}
+	const f32x2 rK0 = pk2(rc.rK0, rc.rK0), rK4 = pk2(rc.rK4, rc.rK4);
+	const f32x2 nK2 = pk2(-rc.cam.K[2], -rc.cam.K[2]), nK5 = pk2(-rc.cam.K[5], -rc.cam.K[5]);
+	f32x2 T[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		T[3 * r + 0] = mul2(H[3 * r + 0], rK0);
+		T[3 * r + 1] = mul2(H[3 * r + 1], rK4);
+		T[3 * r + 2] = add2(H[3 * r + 2], fma2(mul2(nK2, H[3 * r + 0]), rK0, mul2(mul2(nK5, H[3 * r + 1]), rK4)));
+	}
+	const f32x2 K0 = pk2(v0.K0, v1.K0), K2 = pk2(v0.K2, v1.K2), K4 = pk2(v0.K4, v1.K4), K5 = pk2(v0.K5, v1.K5), K8 = pk2(v0.K8, v1.K8);
+	Homog2 o;
+	o.h[0] = fma2(K0, T[0], mul2(K2, T[6]));
+	o.h[1] = fma2(K0, T[1], mul2(K2, T[7]));
+	o.h[2] = fma2(K0, T[2], mul2(K2, T[8]));
+	o.h[3] = fma2(K4, T[3], mul2(K5, T[6]));
+	o.h[4] = fma2(K4, T[4], mul2(K5, T[7]));
+	o.h[5] = fma2(K4, T[5], mul2(K5, T[8]));
+	o.h[6] = mul2(K8, T[6]);
+	o.h[7] = mul2(K8, T[7]);
+	o.h[8] = mul2(K8, T[8]);
+	return o;
+}
+// (H (x, y, 1))_xy / z for both slots: ComputeCorrespondingPoint as inlined at APD.cu:426-432 and :545
+__device__ __forceinline__ void project2(const Homog2 &H, float xf, float yf, float &x0, float &y0, float &x1, float &y1) {
+	const f32x2 XF = pk2(xf, xf), YF = pk2(yf, yf);
+	const f32x2 Z = add2(H.h[8], fma2(H.h[6], XF, mul2(H.h[7], YF)));
+	float z0, z1; unpk2(Z, z0, z1);
+	const f32x2 RZ = pk2(rcpf(z0), rcpf(z1));
+	const f32x2 X = mul2(add2(H.h[2], fma2(H.h[0], XF, mul2(H.h[1], YF))), RZ);
+	const f32x2 Y = mul2(add2(H.h[5], fma2(H.h[3], XF, mul2(H.h[4], YF))), RZ);
+	unpk2(X, x0, x1); unpk2(Y, y0, y1);
+}
+
+// NCC of one window for the two slots of this lane (same reference taps; APD.cu:456-505 / :556-610)
+template <int INC>
+__device__ __forceinline__ void wq_window2(cudaTextureObject_t tex, int lay0, int lay1, const Homog2 &H, bool w0, bool w1,
+                                           int cx, int cy, float inv_w, const float *col, float sum_r, float sum_rr, float &o0, float &o1) {
+	f32x2 TS = 0ull, TSS = 0ull, TRS = 0ull;
+	const float cxf = (float)cx, cyf = (float)cy;         // tap coordinates are small integers: cxf + i == (float)(cx + i) exactly
 	int n = 0;
 #pragma unroll(INC == 5 ? 3 : 1)
 	for (int i = -5; i <= 5; i += INC) {
-		const float xf = (float)(cx + i);
-		const float ax0 = h0[0] * xf, ay0 = h0[3] * xf, az0 = h0[6] * xf;
-		float ax1 = 0.f, ay1 = 0.f, az1 = 0.f;
-		if (NR > 1) { ax1 = h1[0] * xf; ay1 = h1[3] * xf; az1 = h1[6] * xf; }
-		float rs0 = 0.f, ss0 = 0.f, sm0 = 0.f, rs1 = 0.f, ss1 = 0.f, sm1 = 0.f;
+		const float xf = cxf + (float)i;
+		const f32x2 XF = pk2(xf, xf);
+		const f32x2 AX = mul2(H.h[0], XF), AY = mul2(H.h[3], XF), AZ = mul2(H.h[6], XF);
+		f32x2 RS = 0ull, S = 0ull, SS = 0ull;
 #pragma unroll
 		for (int j = -5; j <= 5; j += INC) {
 			const float rp = col[n * kWqPix];
 			++n;
-			const float yf = (float)(cy + j);
+			const float yf = cyf + (float)j;
+			const f32x2 YF = pk2(yf, yf);
+			const f32x2 XS = add2(H.h[2], fma2(H.h[1], YF, AX));
+			const f32x2 YS = add2(H.h[5], fma2(H.h[4], YF, AY));
+			const f32x2 ZS = add2(H.h[8], fma2(H.h[7], YF, AZ));
+			float xs0, xs1, ys0, ys1, zs0, zs1;
+			unpk2(XS, xs0, xs1); unpk2(YS, ys0, ys1); unpk2(ZS, zs0, zs1);
 			float sp0 = 0.f, sp1 = 0.f;
-			if (w0) sp0 = src_tap(tex, layer, h0, ax0, ay0, az0, yf);
-			if (NR > 1) { if (w1) sp1 = src_tap(tex, layer, h1, ax1, ay1, az1, yf); }
-			rs0 = fmaf(rp, sp0, rs0); sm0 += sp0; ss0 = fmaf(sp0, sp0, ss0);
-			if (NR > 1) { rs1 = fmaf(rp, sp1, rs1); sm1 += sp1; ss1 = fmaf(sp1, sp1, ss1); }
+			if (w0) { const float rz = rcpf(zs0); sp0 = tex2DLayered<float>(tex, fmaf(xs0, rz, 0.5f), fmaf(ys0, rz, 0.5f), lay0); }
+			if (w1) { const float rz = rcpf(zs1); sp1 = tex2DLayered<float>(tex, fmaf(xs1, rz, 0.5f), fmaf(ys1, rz, 0.5f), lay1); }
+			const f32x2 SP = pk2(sp0, sp1), RP = pk2(rp, rp);
+			RS = fma2(RP, SP, RS); S = add2(S, SP); SS = fma2(SP, SP, SS);
 		}
-		t0.s += sm0; t0.ss += ss0; t0.rs += rs0;
-		if (NR > 1) { t1.s += sm1; t1.ss += ss1; t1.rs += rs1; }
+		TS = add2(TS, S); TSS = add2(TSS, SS); TRS = add2(TRS, RS);
 	}
-	o0 = ncc_cost(t0, inv_w);
-	if (NR > 1) o1 = ncc_cost(t1, inv_w);
+	NccSums t0 = {sum_r, sum_rr, 0.f, 0.f, 0.f}, t1 = t0;
+	unpk2(TS, t0.s, t1.s); unpk2(TSS, t0.ss, t1.ss); unpk2(TRS, t0.rs, t1.rs);
+	o0 = ncc_cost(t0, inv_w); o1 = ncc_cost(t1, inv_w);
 }
 
 // per-pixel shared-memory columns of the owning warp (stride kWqPix between rows)
@@ -125,48 +211,50 @@ struct WqPixel {
 	const uint32_t *asel;     // [8] selected-view bitmasks of anchors 1..8
 };
 
-// ComputeBilateralNCCNew (APD.cu:400-528) for the two planes of this lane against source view v.
-__device__ __forceinline__ void wq_deform_pair(const Args &a, const RefConst &rc, const ViewConst &vc, int v, const float4 P0, const float4 P1,
+// ComputeBilateralNCCNew (APD.cu:400-528) for the two slots of this lane: plane P0 against source view v0, P1 against v1.
+__device__ __forceinline__ void wq_deform_pair(const Args &a, const RefConst &rc, const ViewConst *sv, int v0, int v1, const float4 P0, const float4 P1,
                                                bool on0, bool on1, const WqPixel &px, float inv36, float inv9, float &out0, float &out1) {
-	const Homog H0 = make_homography(rc, vc, P0), H1 = make_homography(rc, vc, P1);
+	const ViewConst &vc0 = sv[v0], &vc1 = sv[v1];
+	const Homog2 H = make_homography2(rc, vc0, vc1, P0, P1);
 	const short2 self = px.anc[0];
-	bool live0 = on0 && centre_inside(H0, vc, (float)self.x, (float)self.y);
-	bool live1 = on1 && centre_inside(H1, vc, (float)self.x, (float)self.y);
+	bool live0, live1;
+	{
+		float x0, y0, x1, y1;
+		project2(H, (float)self.x, (float)self.y, x0, y0, x1, y1);
+		live0 = on0 && !(x0 >= vc0.wf || x0 < 0.0f || y0 >= vc0.hf || y0 < 0.0f);           // APD.cu:424-435
+		live1 = on1 && !(x1 >= vc1.wf || x1 < 0.0f || y1 >= vc1.hf || y1 < 0.0f);
+	}
 	float cc0 = 0.f, sc0 = 0.f, cc1 = 0.f, sc1 = 0.f; int n0 = 0, n1 = 0;
 	const float Wf = (float)a.W, Hf = (float)a.H;
 #pragma unroll 1
 	for (int k = 0; k < APD_NEIGHBOUR_NUM; ++k) {
 		const short2 q = px.anc[k * kWqPix];
 		const bool valid = !(q.x == -1 || q.y == -1);
-		const float xf = (float)q.x, yf = (float)q.y;
 		bool w0 = false, w1 = false;
-		if (valid && live0) {
-			const float *h = H0.h;
-			const float rz = rcpf(h[8] + fmaf(h[6], xf, h[7] * yf));
-			const float sx = (h[2] + fmaf(h[0], xf, h[1] * yf)) * rz;
-			const float sy = (h[5] + fmaf(h[3], xf, h[4] * yf)) * rz;
-			if (sx < 0.0f || sy < 0.0f || sx >= Wf || sy >= Hf) {
-				if (k == 0) live0 = false;                                                        // APD.cu:437-438
-				else if ((px.asel[(k - 1) * kWqPix] >> v) & 1u) { sc0 += kCostMax; ++n0; }           // APD.cu:439-446
-			} else w0 = true;
-		}
-		if (valid && live1) {
-			const float *h = H1.h;
-			const float rz = rcpf(h[8] + fmaf(h[6], xf, h[7] * yf));
-			const float sx = (h[2] + fmaf(h[0], xf, h[1] * yf)) * rz;
-			const float sy = (h[5] + fmaf(h[3], xf, h[4] * yf)) * rz;
-			if (sx < 0.0f || sy < 0.0f || sx >= Wf || sy >= Hf) {
-				if (k == 0) live1 = false;
-				else if ((px.asel[(k - 1) * kWqPix] >> v) & 1u) { sc1 += kCostMax; ++n1; }
-			} else w1 = true;
+		if (__any_sync(0xffffffffu, valid && (live0 || live1))) {
+			float sx0, sy0, sx1, sy1;
+			project2(H, (float)q.x, (float)q.y, sx0, sy0, sx1, sy1);
+			const uint32_t sel = (k == 0) ? 0u : px.asel[(k - 1) * kWqPix];
+			if (valid && live0) {
+				if (sx0 < 0.0f || sy0 < 0.0f || sx0 >= Wf || sy0 >= Hf) {
+					if (k == 0) live0 = false;                                                    // APD.cu:437-438
+					else if ((sel >> v0) & 1u) { sc0 += kCostMax; ++n0; }                          // APD.cu:439-446
+				} else w0 = true;
+			}
+			if (valid && live1) {
+				if (sx1 < 0.0f || sy1 < 0.0f || sx1 >= Wf || sy1 >= Hf) {
+					if (k == 0) live1 = false;
+					else if ((sel >> v1) & 1u) { sc1 += kCostMax; ++n1; }
+				} else w1 = true;
+			}
 		}
 		if (!__any_sync(0xffffffffu, w0 || w1)) continue;          // warp-uniform
 		float c0 = 0.f, c1 = 0.f;
 		if (k == 0)
-			wq_window<2, 2>(a.img_tex, v + 1, H0.h, H1.h, w0, w1, q.x, q.y, inv36, px.refc, px.refc[kRowSum * kWqPix], px.refc[(kRowSum + 1) * kWqPix], c0, c1);
+			wq_window2<2>(a.img_tex, v0 + 1, v1 + 1, H, w0, w1, q.x, q.y, inv36, px.refc, px.refc[kRowSum * kWqPix], px.refc[(kRowSum + 1) * kWqPix], c0, c1);
 		else
-			wq_window<5, 2>(a.img_tex, v + 1, H0.h, H1.h, w0, w1, q.x, q.y, inv9, px.refc + (kOwnTaps + 9 * (k - 1)) * kWqPix,
-			                px.refc[(kRowSum + 2 * k) * kWqPix], px.refc[(kRowSum + 2 * k + 1) * kWqPix], c0, c1);
+			wq_window2<5>(a.img_tex, v0 + 1, v1 + 1, H, w0, w1, q.x, q.y, inv9, px.refc + (kOwnTaps + 9 * (k - 1)) * kWqPix,
+			              px.refc[(kRowSum + 2 * k) * kWqPix], px.refc[(kRowSum + 2 * k + 1) * kWqPix], c0, c1);
 		if (w0) { if (k == 0) cc0 = c0; else { sc0 += c0; ++n0; } }
 		if (w1) { if (k == 0) cc1 = c1; else { sc1 += c1; ++n1; } }
 	}
@@ -193,7 +281,9 @@ __device__ __forceinline__ void wq_hypothesis(const Args &a, const RefConst &rc,
 	in_range = d >= a.depth_min && d <= a.depth_max;
 }
 
-__global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int iter, const int color, int *work) {
+// MINB = resident blocks per SM the register allocation is sized for (4: 128 registers, 3: 168)
+template <int MINB>
+__global__ void __launch_bounds__(kWqNT, MINB) k_weak_q(const Args a, const int iter, const int color, int *work) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	RefConst *sr = reinterpret_cast<RefConst *>(smem_raw);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
@@ -271,30 +361,36 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 		const unsigned flags = astrong[0] & 0xFFu;
 		auto cand_pos = [&](int k) { const short2 q = anc[(k + 1) * kWqPix]; return q.x + q.y * W; };
 
-		// ---- quad state machine. phase 0: cost matrix (lane l: candidates l, l+4; all S views);
-		//      phase 1: current plane (lane 0) + fit plane (lane 1) over the sampled views;
-		//      phase 2: the five refinement hypotheses (lanes 0..3 + lane 0's second slot); phase 3: done
+		// ---- quad state machine; every step each lane carries two evaluations ("slots") through wq_deform_pair.
+		//  phase 0  cost matrix: lane l = candidates l (slot 0) and l+4 (slot 1) against view v, one view per step;
+		//  phase 1  current plane (even lanes) and fit plane (odd lanes): lane pair l>>1 and the slot pick one of the next four
+		//           sampled views, so a step covers four views of both planes; sums are formed in view order afterwards;
+		//  phase 2  the five refinement hypotheses: every lane is a worker that walks the sampled views of ITS hypothesis,
+		//           two per step (slots), and stops when the partial sum can no longer beat the current cost; hypothesis 2
+		//           waits for the first lane that becomes free;   phase 3  done.
 		int phase = 0;
-		uint32_t m = (S >= 32) ? 0xffffffffu : ((1u << S) - 1u);
-		float4 T0 = make_float4(0.f, 0.f, 1.f, 1.f), T1 = T0;
-		bool on0 = (flags >> ql) & 1u, on1 = (flags >> (ql + 4)) & 1u;
-		if (on0) T0 = a.planes[cand_pos(ql)];
-		if (on1) T1 = a.planes[cand_pos(ql + 4)];
-		float acc0 = 0.f, acc1 = 0.f; bool pruned0 = false, pruned1 = false;
+		uint32_t m = (S >= 32) ? 0xffffffffu : ((1u << S) - 1u);      // phases 0/1: views still to do (quad-uniform)
+		float4 T = make_float4(0.f, 0.f, 1.f, 1.f), Tb = T;
+		const bool cand0 = (flags >> ql) & 1u, cand1 = (flags >> (ql + 4)) & 1u;
+		if (cand0) T = a.planes[cand_pos(ql)];
+		if (cand1) Tb = a.planes[cand_pos(ql + 4)];
 		float limit = kInf;
 		Rng rng; rng.v0 = rng.v1 = rng.v2 = rng.v3 = rng.v4 = rng.d = 0u;
 		VW vw; vw.lo = 0ull; vw.hi = 0ull;
 		uint32_t temp_sel = 0u; float inv_wn = 0.f, best_cost = 0.f; int best_k = 0;
-		float4 pl_now = make_float4(0.f, 0.f, 1.f, 1.f), fit = pl_now;
+		float4 pl_now = make_float4(0.f, 0.f, 1.f, 1.f);
 		float cost_now = 0.f, cost_stored = 0.f, depth_now = 0.f, d_fit = 0.f;
 		bool have_fit = false, fit_ok = false, sel_write = false;
+		float acc_cur = 0.f, acc_fit = 0.f; bool pr_cur = false, pr_fit = false;                 // phase 1 (replicated in the quad)
+		uint32_t my_m = 0u; float my_acc = 0.f, res_first = 0.f; bool my_busy = false, second = false, pending2 = false;   // phase 2 worker
+		int owner2 = -1; unsigned q_busy = 0u;
 		Refine5 rf; rf.depth_rand = rf.depth_pert = rf.d0 = 0.f; rf.n_rand = rf.n_pert = rf.n0 = pl_now;
 
 #pragma unroll 1
-		for (int step = 0; step < 3 * S + 8; ++step) {
+		for (int step = 0; step < 3 * S + 16; ++step) {
 			// ---- phase transitions (quad-uniform; quads of a warp may be in different phases)
 #pragma unroll 1
-			while (phase < 3 && m == 0u) {
+			while (phase < 3 && ((phase < 2) ? (m == 0u) : (q_busy == 0u && !pending2))) {
 				if (phase == 0) {
 					__syncwarp(qmask);                                     // the quad's matrix entries are visible
 					// view selection (APD.cu:1365-1434): priors from every existing anchor, STRONG or not
@@ -345,8 +441,8 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 							if (w == 0) continue;
 							float c0 = CM(ql, v), c1 = CM(ql + 4, v);
 							if (a.geom) {
-								c0 = on0 ? fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, T0, xf, yf), c0) : fmaf(a.geom_factor, 3.0f, c0);
-								c1 = on1 ? fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, T1, xf, yf), c1) : fmaf(a.geom_factor, 3.0f, c1);
+								c0 = cand0 ? fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, T, xf, yf), c0) : fmaf(a.geom_factor, 3.0f, c0);
+								c1 = cand1 ? fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, Tb, xf, yf), c1) : fmaf(a.geom_factor, 3.0f, c1);
 							}
 							s0 = fmaf((float)w, c0, s0); s1 = fmaf((float)w, c1, s1);
 						}
@@ -361,17 +457,15 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 					// phase 1: the current plane and the fit plane (PlaneHypothesisRefinementWeak returns before any draw
 					// when the fit plane is all-zero, APD.cu:912-914)
 					pl_now = a.planes[center];
-					fit = a.fit_planes[center];
+					const float4 fit = a.fit_planes[center];
 					have_fit = !(fit.x == 0.0f && fit.y == 0.0f && fit.z == 0.0f);
 					d_fit = plane_depth(rc, fit, xf, yf);
 					fit_ok = have_fit && d_fit >= a.depth_min && d_fit <= a.depth_max;
-					T0 = (ql == 1) ? fit : pl_now;
-					on0 = (ql == 0) || (ql == 1 && fit_ok); on1 = false;
-					acc0 = acc1 = 0.f; pruned0 = pruned1 = false; limit = kInf;
+					T = (ql & 1) ? fit : pl_now;
+					acc_cur = acc_fit = 0.f; pr_cur = pr_fit = false; limit = kInf;
 					m = temp_sel; phase = 1;
 				} else if (phase == 1) {
-					const float tc_cur = __shfl_sync(qmask, acc0, 0, 4) * inv_wn;
-					const float tc_fit = __shfl_sync(qmask, acc0, 1, 4) * inv_wn;
+					const float tc_cur = acc_cur * inv_wn, tc_fit = acc_fit * inv_wn;
 					cost_now = tc_cur; cost_stored = tc_cur;
 					depth_now = plane_depth(rc, pl_now, xf, yf);
 					if ((flags >> best_k) & 1u) {                                       // APD.cu:1474-1486
@@ -382,7 +476,7 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 						}
 					}
 					if (have_fit) {
-						if (fit_ok && tc_fit < cost_now) { depth_now = d_fit; pl_now = fit; cost_now = tc_fit; }   // APD.cu:916-935
+						if (fit_ok && tc_fit < cost_now) { depth_now = d_fit; pl_now = a.fit_planes[center]; cost_now = tc_fit; }   // APD.cu:916-935
 						rf.depth_rand = fmaf(rng_uniform(rng), a.depth_max - a.depth_min, a.depth_min);
 						rf.n_rand = random_normal(rc, xf, yf, rng, depth_now);
 						const float lo = depth_now * (1.0f - 0.02f);
@@ -390,22 +484,24 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 						rf.depth_pert = fmaf(span, rng_uniform(rng), lo);
 						rf.n_pert = perturbed_normal(rc, xf, yf, pl_now, rng);
 						rf.n0 = pl_now; rf.d0 = depth_now;
-						// lanes 0..3 take hypotheses 3, 4 (the two near the current plane), 0, 1; lane 0's second slot takes 2
-						float d; bool ok;
-						wq_hypothesis(a, rc, rf, (ql + 3) % 5, xf, yf, T0, d, ok);
-						on0 = ok;
-						on1 = false;
-						if (ql == 0) { wq_hypothesis(a, rc, rf, 2, xf, yf, T1, d, ok); on1 = ok; }
-						acc0 = acc1 = 0.f; pruned0 = pruned1 = false; limit = cost_now;
-						m = temp_sel; phase = 2;
-						// nothing in range anywhere in the quad: no evaluation at all
-						if ((__ballot_sync(qmask, on0 || on1) & qmask) == 0u) m = 0u;
+						// lanes 0..3 start with hypotheses 3, 4 (the two near the current plane), 0, 1; hypothesis 2 is pending
+						float d; bool ok, ok2; float4 t2;
+						wq_hypothesis(a, rc, rf, (ql + 3) % 5, xf, yf, T, d, ok);
+						wq_hypothesis(a, rc, rf, 2, xf, yf, t2, d, ok2);
+						my_m = temp_sel; my_acc = 0.f; my_busy = ok && temp_sel != 0u;        // out of range: never evaluated
+						pending2 = ok2 && temp_sel != 0u; owner2 = -1; second = false; res_first = 0.f;
+						limit = cost_now;
+						q_busy = __ballot_sync(qmask, my_busy) & qmask;
+						phase = 2;
 					} else phase = 3;
 				} else {   // phase == 2: adopt in the reference's order, strict <
+					const float mine = second ? res_first : my_acc;
 #pragma unroll 1
 					for (int i = 0; i < 5; ++i) {
-						const int src = (i == 2) ? 0 : ((i + 2) % 5);           // lane that evaluated hypothesis i
-						const float tci = __shfl_sync(qmask, (i == 2) ? acc1 : acc0, src, 4) * inv_wn;
+						float val;
+						if (i == 2) val = __shfl_sync(qmask, my_acc, owner2 < 0 ? 0 : owner2, 4);
+						else val = __shfl_sync(qmask, mine, (i + 2) % 5, 4);               // lane that started with hypothesis i
+						const float tci = val * inv_wn;
 						float4 t; float d; bool ok;
 						wq_hypothesis(a, rc, rf, i, xf, yf, t, d, ok);
 						if (ok && tci < cost_now) { depth_now = d; pl_now = t; cost_now = tci; }
@@ -414,33 +510,77 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 				}
 			}
 			if (!__any_sync(0xffffffffu, phase < 3)) break;
-			const bool want = phase < 3;
-			const int v = want ? (__ffs(m) - 1) : 0;
-			m &= m - 1u;
-			const bool l0 = want && on0 && !pruned0, l1 = want && on1 && !pruned1;
+			// ---- hypothesis 2 takes the first free lane of its quad
+			if (phase == 2 && pending2) {
+				const unsigned free_lanes = (~q_busy) & qmask;
+				if (free_lanes != 0u) {
+					owner2 = (__ffs(free_lanes) - 1) & 3;
+					if (ql == owner2) {
+						float d; bool ok;
+						res_first = my_acc; second = true;
+						wq_hypothesis(a, rc, rf, 2, xf, yf, T, d, ok);
+						my_m = temp_sel; my_acc = 0.f; my_busy = true;
+					}
+					pending2 = false;
+					q_busy |= 1u << ((lane & ~3) + owner2);
+				}
+			}
+			// ---- this step's two slots
+			int v0 = 0, v1 = 0; bool s0 = false, s1 = false;
+			float4 P1 = T;
+			if (phase == 0) {
+				v0 = v1 = __ffs(m) - 1; m &= m - 1u;
+				s0 = cand0; s1 = cand1; P1 = Tb;
+			} else if (phase == 1) {
+				uint32_t mm = m;
+				if (ql >> 1) mm &= mm - 1u;
+				const bool mine = ((ql & 1) == 0) ? !pr_cur : (fit_ok && !pr_fit);
+				if (mm) { v0 = __ffs(mm) - 1; s0 = mine; }
+				mm &= mm - 1u; mm &= mm - 1u;
+				if (mm) { v1 = __ffs(mm) - 1; s1 = mine; }
+			} else if (phase == 2 && my_busy) {
+				v0 = __ffs(my_m) - 1; my_m &= my_m - 1u; s0 = true;
+				if (my_m) { v1 = __ffs(my_m) - 1; my_m &= my_m - 1u; s1 = true; }
+			}
+			__syncwarp();
 			float c0, c1;
-			wq_deform_pair(a, rc, sv[v], v, T0, T1, l0, l1, wp, inv36, inv9, c0, c1);
+			wq_deform_pair(a, rc, sv, v0, v1, T, P1, s0, s1, wp, inv36, inv9, c0, c1);
 			if (phase == 0) {
 				// a missing candidate keeps the reference's partially initialised row: `cost_array[8][32] = {2.0f}` sets
 				// [0][0] only (APD.cu:1345)
-				CM(ql, v) = on0 ? c0 : ((ql == 0 && v == 0) ? 2.0f : 0.0f);
-				CM(ql + 4, v) = on1 ? c1 : 0.0f;
-			} else if (want) {
-				const float w = (float)vw_get(vw, v);
-				if (l0) {
-					if (a.geom) c0 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, T0, xf, yf), c0);
-					acc0 = fmaf(w, c0, acc0);
-					if (prune && acc0 * inv_wn >= limit) pruned0 = true;
+				CM(ql, v0) = cand0 ? c0 : ((ql == 0 && v0 == 0) ? 2.0f : 0.0f);
+				CM(ql + 4, v0) = cand1 ? c1 : 0.0f;
+			} else if (phase == 1) {
+				if (a.geom) {
+					if (s0) c0 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v0], v0 + 1, T, xf, yf), c0);
+					if (s1) c1 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v1], v1 + 1, T, xf, yf), c1);
 				}
-				if (l1) {
-					if (a.geom) c1 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, T1, xf, yf), c1);
-					acc1 = fmaf(w, c1, acc1);
-					if (prune && acc1 * inv_wn >= limit) pruned1 = true;
+				// the four views of this step in ascending order: position p sits in slot p>>1 of lane pair p&1
+#pragma unroll
+				for (int p = 0; p < 4; ++p) {
+					const float cc = __shfl_sync(qmask, (p >> 1) ? c1 : c0, 2 * (p & 1), 4);
+					const float cf = __shfl_sync(qmask, (p >> 1) ? c1 : c0, 2 * (p & 1) + 1, 4);
+					if (m != 0u) {
+						const int v = __ffs(m) - 1; m &= m - 1u;
+						const float w = (float)vw_get(vw, v);
+						if (!pr_cur) { acc_cur = fmaf(w, cc, acc_cur); if (prune && acc_cur * inv_wn >= limit) pr_cur = true; }
+						if (fit_ok && !pr_fit) { acc_fit = fmaf(w, cf, acc_fit); if (prune && acc_fit * inv_wn >= limit) pr_fit = true; }
+					}
 				}
+			} else if (phase == 2) {
+				if (s0) {
+					if (a.geom) c0 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v0], v0 + 1, T, xf, yf), c0);
+					my_acc = fmaf((float)vw_get(vw, v0), c0, my_acc);
+					if (prune && my_acc * inv_wn >= limit) my_busy = false;
+				}
+				if (s1 && my_busy) {
+					if (a.geom) c1 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v1], v1 + 1, T, xf, yf), c1);
+					my_acc = fmaf((float)vw_get(vw, v1), c1, my_acc);
+					if (prune && my_acc * inv_wn >= limit) my_busy = false;
+				}
+				if (my_busy && my_m == 0u) my_busy = false;
+				q_busy = __ballot_sync(qmask, my_busy) & qmask;
 			}
-			// a quad whose hypotheses are all out of the race stops walking its views
-			const unsigned running = __ballot_sync(0xffffffffu, (on0 && !pruned0) || (on1 && !pruned1));
-			if (phase != 0 && (running & qmask) == 0u) m = 0u;
 		}
 
 		// ---- commit (APD.cu:1488-1507)
@@ -454,30 +594,38 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 			if (sel_write) a.sel_views[center] = temp_sel;
 			if (adopt) a.planes[center] = pl_now;
 		}
-		// "update cost with old method": plain NCC of the committed plane over the sampled views, lanes = views
+		// "update cost with old method": plain NCC of the committed plane over the sampled views; the lanes and their two
+		// slots take eight views at a time, the sum is formed in view order
 		float facc = 0.0f;
 		uint32_t fm = temp_sel;
 #pragma unroll 1
 		while (__any_sync(0xffffffffu, fm != 0u)) {
 			uint32_t mm = fm;
 			for (int t = 0; t < ql; ++t) mm &= mm - 1u;
-			const int v = mm ? (__ffs(mm) - 1) : -1;
-			const int vv = v < 0 ? 0 : v;
-			const Homog Hm = make_homography(rc, sv[vv], final_plane);
-			const bool w = v >= 0 && centre_inside(Hm, sv[vv], xf, yf);
-			float c = kCostMax, dummy = 0.f;
-			if (__any_sync(0xffffffffu, w)) {
-				float cw = 0.f;
-				wq_window<2, 1>(a.img_tex, vv + 1, Hm.h, Hm.h, w, false, px, py, inv36, refc, refc[kRowSum * kWqPix], refc[(kRowSum + 1) * kWqPix], cw, dummy);
-				if (w) c = cw;
+			const int va = mm ? (__ffs(mm) - 1) : -1;
+			mm &= mm - 1u; mm &= mm - 1u; mm &= mm - 1u; mm &= mm - 1u;
+			const int vb = mm ? (__ffs(mm) - 1) : -1;
+			const int ia = va < 0 ? 0 : va, ib = vb < 0 ? 0 : vb;
+			const Homog2 H = make_homography2(rc, sv[ia], sv[ib], final_plane, final_plane);
+			float x0, y0, x1, y1;
+			project2(H, xf, yf, x0, y0, x1, y1);
+			const bool wa = va >= 0 && !(x0 >= sv[ia].wf || x0 < 0.0f || y0 >= sv[ia].hf || y0 < 0.0f);
+			const bool wb = vb >= 0 && !(x1 >= sv[ib].wf || x1 < 0.0f || y1 >= sv[ib].hf || y1 < 0.0f);
+			float ca = kCostMax, cb = kCostMax;
+			if (__any_sync(0xffffffffu, wa || wb)) {
+				float ta = 0.f, tb = 0.f;
+				wq_window2<2>(a.img_tex, ia + 1, ib + 1, H, wa, wb, px, py, inv36, refc, refc[kRowSum * kWqPix], refc[(kRowSum + 1) * kWqPix], ta, tb);
+				if (wa) ca = ta;
+				if (wb) cb = tb;
 			}
 #pragma unroll
-			for (int t = 0; t < 4; ++t) {
-				const float ct = __shfl_sync(0xffffffffu, c, t, 4);
-				const int vt = __shfl_sync(0xffffffffu, v, t, 4);
+			for (int t = 0; t < 8; ++t) {
+				const float ct = __shfl_sync(0xffffffffu, (t < 4) ? ca : cb, t & 3, 4);
+				const int vt = __shfl_sync(0xffffffffu, (t < 4) ? va : vb, t & 3, 4);
 				if (vt >= 0) facc = fmaf((float)vw_get(vw, vt), ct, facc);
 			}
-			fm &= fm - 1u; fm &= fm - 1u; fm &= fm - 1u; fm &= fm - 1u;
+#pragma unroll
+			for (int t = 0; t < 8; ++t) fm &= fm - 1u;
 		}
 		if (alive && ql == 0) a.costs[center] = facc * inv_wn;
 	}
@@ -487,30 +635,37 @@ __global__ void __launch_bounds__(kWqNT, 4) k_weak_q(const Args a, const int ite
 
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_weak_lists(cudaStream_t st, const Args &a, bool split) {
-	dim3 g((a.W + 31) / 32, (a.H + 7) / 8);
+	const int tiles_x = (a.W + 31) / 32, tiles_y = (a.H + 7) / 8;
+	const int supers_x = (tiles_x + kSuperX - 1) / kSuperX, supers_y = (tiles_y + kSuperY - 1) / kSuperY;
+	const unsigned g = (unsigned)(supers_x * supers_y * kSuperX * kSuperY);
 	if (split) {
 		cudaError_t e = cudaMemsetAsync(a.wctrl, 0, 2 * sizeof(int), st);
 		if (e != cudaSuccess) return e;
-		k_weak_lists<true><<<g, 128, 0, st>>>(a);
+		k_weak_lists<true><<<g, 128, 0, st>>>(a, tiles_x, tiles_y, supers_x);
 	} else {
 		cudaError_t e = cudaMemsetAsync(a.wctrl + 2, 0, sizeof(int), st);
 		if (e != cudaSuccess) return e;
-		k_weak_lists<false><<<g, 128, 0, st>>>(a);
+		k_weak_lists<false><<<g, 128, 0, st>>>(a, tiles_x, tiles_y, supers_x);
 	}
 	return cudaGetLastError();
 }
 
+template <int MINB>
+static cudaError_t launch_weak_q_t(cudaStream_t st, const Args &a, int iter, int color, int work_slot, int num_sms, size_t smem) {
+	cudaError_t e = cudaFuncSetAttribute(k_weak_q<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_weak_q<MINB>, kWqNT, smem);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) per_sm = 1;
+	k_weak_q<MINB><<<num_sms * per_sm, kWqNT, smem, st>>>(a, iter, color, a.wctrl + kWorkBase + work_slot);
+	return cudaGetLastError();
+}
 cudaError_t launch_weak_q(cudaStream_t st, const Args &a, int iter, int color, int work_slot, int num_sms) {
 	const size_t smem = sizeof(RefConst) + (size_t)a.S * sizeof(ViewConst) + (size_t)(kWqNT / 32) * wq_warp_words(a.S) * 4;
 	if (smem > 227 * 1024) return cudaErrorInvalidValue;
-	cudaError_t e = cudaFuncSetAttribute(k_weak_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
-	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_weak_q, kWqNT, smem);
-	if (e != cudaSuccess) return e;
-	if (per_sm < 1) per_sm = 1;
-	k_weak_q<<<num_sms * per_sm, kWqNT, smem, st>>>(a, iter, color, a.wctrl + kWorkBase + work_slot);
-	return cudaGetLastError();
+	static const int minb = [] { const char *e = getenv("APD_WQ_BLOCKS"); return e ? atoi(e) : 3; }();   // measured: 168 registers without spills (3 blocks) beat 128 with spills (4): 5.8 vs 6.8 ms at 1555x1036
+	return minb == 3 ? launch_weak_q_t<3>(st, a, iter, color, work_slot, num_sms, smem) : launch_weak_q_t<4>(st, a, iter, color, work_slot, num_sms, smem);
 }
 
 }  // namespace apd

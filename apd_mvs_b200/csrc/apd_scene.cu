@@ -79,6 +79,7 @@ struct Problem { int ref; std::vector<int> srcs; };
 
 struct apd_scene {
 	int device = 0, n_views = 0, W = 0, H = 0;
+	int round_limit = 1000;      // main.cpp:81: halve until the larger image side is <= 1000
 	uint64_t seed = 0;
 	cudaStream_t stream = nullptr;
 	std::vector<float *> full, scaled;        // device images, full size and current round's size
@@ -100,9 +101,9 @@ static thread_local std::string g_scene_null = "null scene handle";
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { s->err = std::string(#call) + ": " + cudaGetErrorString(e_); return APD_E_CUDA; } } while (0)
 static int sfail(apd_scene_handle s, int code, const std::string &msg) { if (s) s->err = msg; return code; }
 
-static int round_num_for(int W, int H) {   // ComputeRoundNum, main.cpp:72-88
+static int round_num_for(int W, int H, int limit) {   // ComputeRoundNum, main.cpp:72-88 (limit = 1000 there)
 	int max_size = W > H ? W : H, rounds = 1;
-	while (max_size > 1000) { max_size /= 2; rounds++; }
+	while (max_size > limit) { max_size /= 2; rounds++; }
 	return rounds;
 }
 static int scale_size_for(int rounds, int round) { return 1 << (rounds - 1 - round); }   // main.cpp:188
@@ -179,11 +180,19 @@ extern "C" int apd_scene_add_problem(apd_scene_handle s, int ref_view, const int
 	return APD_OK;
 }
 
-extern "C" int apd_scene_num_rounds(apd_scene_handle s) { return s ? round_num_for(s->W, s->H) : 0; }
+extern "C" int apd_scene_set_round_limit(apd_scene_handle s, int max_size) {
+	if (!s) return APD_E_ARG;
+	if (max_size < 16) return sfail(s, APD_E_ARG, "round limit must be >= 16");
+	if (s->eng) return sfail(s, APD_E_STATE, "the schedule is fixed once a pass has run");
+	s->round_limit = max_size;
+	return APD_OK;
+}
+
+extern "C" int apd_scene_num_rounds(apd_scene_handle s) { return s ? round_num_for(s->W, s->H, s->round_limit) : 0; }
 
 extern "C" int apd_scene_round_size(apd_scene_handle s, int round, int *width, int *height) {
 	if (!s || !width || !height) return APD_E_ARG;
-	const int rounds = round_num_for(s->W, s->H);
+	const int rounds = round_num_for(s->W, s->H, s->round_limit);
 	if (round < 0 || round >= rounds) return APD_E_ARG;
 	scaled_size(s->W, s->H, scale_size_for(rounds, round), width, height);
 	return APD_OK;
@@ -191,7 +200,7 @@ extern "C" int apd_scene_round_size(apd_scene_handle s, int round, int *width, i
 
 extern "C" int apd_scene_pass_params(apd_scene_handle s, int round, int pass, apd_params *p) {
 	if (!s || !p || pass < 0 || pass > 3) return APD_E_ARG;
-	const int rounds = round_num_for(s->W, s->H);
+	const int rounds = round_num_for(s->W, s->H, s->round_limit);
 	if (round < 0 || round >= rounds) return APD_E_ARG;
 	apd_default_params(p);
 	const int i = round;
@@ -217,7 +226,7 @@ extern "C" int apd_scene_pass_params(apd_scene_handle s, int round, int pass, ap
 
 // Build the round's pyramid level and engine (called when the round changes).
 static int enter_round(apd_scene_handle s, int round) {
-	const int rounds = round_num_for(s->W, s->H);
+	const int rounds = round_num_for(s->W, s->H, s->round_limit);
 	const int scale = scale_size_for(rounds, round);
 	int rw, rh; scaled_size(s->W, s->H, scale, &rw, &rh);
 	for (int v = 0; v < s->n_views; ++v) if (!s->have_view[v]) return sfail(s, APD_E_STATE, "every view needs apd_scene_set_view first");
@@ -396,7 +405,7 @@ extern "C" int apd_scene_run(apd_scene_handle s) {
 	if (s->problems.empty()) return sfail(s, APD_E_STATE, "no problems");
 	timing_begin(s);
 	const auto t0 = std::chrono::steady_clock::now();
-	const int rounds = round_num_for(s->W, s->H);
+	const int rounds = round_num_for(s->W, s->H, s->round_limit);
 	int rc = APD_OK;
 	for (int i = 0; i < rounds && rc == APD_OK; ++i)
 		for (int pass = 0; pass < 4 && rc == APD_OK; ++pass) rc = run_pass(s, i, pass);

@@ -20,6 +20,7 @@ def _bind(lib):
     lib.apd_fusion_set_view_planes.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp]
     lib.apd_fusion_add_problem.argtypes = [vp, ci, C.POINTER(ci), ci]
     lib.apd_fusion_run.argtypes = [vp]
+    lib.apd_fusion_run_tat.argtypes = [vp, ci]
     lib.apd_fusion_num_points.argtypes = [vp]; lib.apd_fusion_num_points.restype = C.c_longlong
     lib.apd_fusion_get_points.argtypes = [vp, vp, vp]
     lib.apd_fusion_write_ply.argtypes = [vp, C.c_char_p]
@@ -50,8 +51,13 @@ class Fusion:
         arr = (C.c_int * max(len(srcs), 1))(*srcs)
         self._ck(self.L.apd_fusion_add_problem(self._h, ref, arr, len(srcs)))
 
-    def RunFusion(self):
-        self._ck(self.L.apd_fusion_run(self._h))
+    def RunFusion(self, variant: str = "eth"):
+        """variant: "eth" = RunFusion (APD.cpp:826-977), "tat_intermediate" / "tat_advanced" = RunFusion_TAT_Intermediate /
+        RunFusion_TAT_advanced (APD.cpp:979-1296)."""
+        if variant == "eth":
+            self._ck(self.L.apd_fusion_run(self._h))
+        else:
+            self._ck(self.L.apd_fusion_run_tat(self._h, {"tat_intermediate": 1, "tat_advanced": 2}[variant]))
         n = self.L.apd_fusion_num_points(self._h)
         xyz = np.empty((n, 3), np.float32); col = np.empty((n, 3), np.float32)
         self._ck(self.L.apd_fusion_get_points(self._h, xyz.ctypes.data, col.ctypes.data))

@@ -20,6 +20,7 @@ def _bind(lib):
     lib.apd_scene_last_error.argtypes = [vp]; lib.apd_scene_last_error.restype = C.c_char_p
     lib.apd_scene_set_view.argtypes = [vp, ci, vp, C.c_size_t, vp]
     lib.apd_scene_add_problem.argtypes = [vp, ci, C.POINTER(ci), ci]
+    lib.apd_scene_set_round_limit.argtypes = [vp, ci]
     lib.apd_scene_num_rounds.argtypes = [vp]
     lib.apd_scene_round_size.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
     lib.apd_scene_pass_params.argtypes = [vp, ci, ci, C.POINTER(E.PatchMatchParams)]
@@ -41,9 +42,10 @@ def _bind(lib):
 class Scene:
     """One dense_folder of the reference: images + cameras of all views and the pair list."""
 
-    def __init__(self, images, cameras, pairs, seed: int = 1234567, device: int = 0):
+    def __init__(self, images, cameras, pairs, seed: int = 1234567, device: int = 0, round_limit: int | None = None):
         """images: [n_views, H, W] float32 (numpy, or a torch CUDA tensor on `device`); cameras: CAMERA_DTYPE[n_views];
-        pairs: list of (ref_view, [src_views...]) in pair.txt order."""
+        pairs: list of (ref_view, [src_views...]) in pair.txt order; round_limit: replaces the literal 1000 of
+        ComputeRoundNum (main.cpp:81)."""
         self.L = _bind(E.lib())
         n, H, W = images.shape
         self.n_views, self.H, self.W = int(n), int(H), int(W)
@@ -52,6 +54,8 @@ class Scene:
         rc = self.L.apd_scene_create(C.byref(self._h), device, self.n_views, self.W, self.H, seed)
         if rc:
             raise E.ApdError(f"apd_scene_create failed ({rc})")
+        if round_limit is not None:
+            self._ck(self.L.apd_scene_set_round_limit(self._h, int(round_limit)))
         cams = np.ascontiguousarray(cameras, dtype=CAMERA_DTYPE)
         for v in range(self.n_views):
             if isinstance(images, np.ndarray):
@@ -172,12 +176,13 @@ def ring_pairs(n_views: int, n_src: int):
 
 class ShardedScene:
     """The schedule of main.cpp:168-217 over `world` ranks: problem k belongs to rank k % world; every
-    rank holds all images and cameras (one broadcast at setup) and, after each pass, the owners broadcast the depth
-    maps they produced - the only data another rank's next pass reads (geometric term, APD.cpp:492-510). Priors
-    (normals, pixel states, selected views) never leave their owner. Within a rank problems keep pair-list order, so a
-    rank sees its own earlier results of the same pass (as the reference does) and its peers' results of the previous
-    pass: the sharded schedule is block-Jacobi where the reference is Gauss-Seidel, which is why parity
-    is defined per (problem, pass) on identical inputs (the tests emulate this visibility rule around the reference).
+    rank holds all images and cameras (one broadcast at setup) and, after each pass, ONE all-gather hands every rank the
+    depth maps the others produced - the only data another rank's next pass reads (geometric term, APD.cpp:492-510).
+    Priors (normals, pixel states, selected views) never leave their owner. Within a rank problems keep pair-list order,
+    so a rank sees its own earlier results of the same pass (as the reference does) and its peers' results of the
+    previous pass: the sharded schedule is block-Jacobi where the reference is Gauss-Seidel, which is why
+    parity is defined per (problem, pass) on identical inputs (the tests emulate this visibility rule around the
+    reference).
 
     `backend` needs process(round, pass, k), depth_tensor(view, w, h), mark_result(view, w, h), round_size(round), sync();
     `Scene` is the GPU backend, the CPU tests use a numpy stand-in."""
@@ -186,9 +191,11 @@ class ShardedScene:
         self.b, self.pairs, self.rank, self.world, self.rounds = backend, pairs, rank, world, rounds
         self.process_ms = 0.0
         self.exchange_ms = 0.0
+        self.wait_ms = 0.0
         refs = [r for r, _ in pairs]
         if len(set(refs)) != len(refs):
             raise ValueError("a view may be the reference of one problem only (pair.txt has one entry per image)")
+        self._stage = {}
 
     def owner(self, problem: int) -> int:
         return problem % self.world
@@ -201,28 +208,47 @@ class ShardedScene:
         t0 = time.perf_counter()
         for k in self.my_problems():
             self.b.process(round_, pass_, k)
+        self.b.sync()
         t1 = time.perf_counter()
-        self.exchange(round_)
         self.process_ms += 1e3 * (t1 - t0)
-        self.exchange_ms += 1e3 * (time.perf_counter() - t1)      # includes waiting for the slowest owner
+        self.exchange(round_)
 
     def exchange(self, round_: int):
+        """One all-gather per pass: every rank packs the depth maps it owns into a contiguous stack (slot j = its j-th
+        problem; ranks with one problem less pad the last slot), the gathered [world, slots, h, w] stack is unpacked into
+        the peers' result buffers in place."""
         if self.world == 1:
             return
+        import time
+        import torch
         import torch.distributed as dist
         w, h = self.b.round_size(round_)
-        work = []
+        n = len(self.pairs)
+        slots = (n + self.world - 1) // self.world
+        mine = self.my_problems()
+        ref0 = self.b.depth_tensor(self.pairs[0][0], w, h)
+        key = (w, h)
+        if key not in self._stage:
+            self._stage = {key: (torch.zeros((slots, h, w), dtype=ref0.dtype, device=ref0.device),
+                                 torch.empty((self.world, slots, h, w), dtype=ref0.dtype, device=ref0.device))}
+        stage, gathered = self._stage[key]
+        for j, k in enumerate(mine):
+            stage[j].copy_(self.b.depth_tensor(self.pairs[k][0], w, h))
+        self.b.sync()
+        t0 = time.perf_counter()
+        dist.barrier()                              # waiting for the slowest owner, reported apart from the transfer
+        t1 = time.perf_counter()
+        dist.all_gather(list(gathered.unbind(0)), stage)
         for k, (ref, _) in enumerate(self.pairs):
-            t = self.b.depth_tensor(ref, w, h)
-            work.append(dist.broadcast(t, src=self.owner(k), async_op=True))
-        for wk in work:
-            wk.wait()
-        self.b.sync()        # the scene's own stream must not run ahead of the collective's stream
-        for k, (ref, _) in enumerate(self.pairs):
-            if self.owner(k) != self.rank:
+            r = self.owner(k)
+            if r != self.rank:
+                self.b.depth_tensor(ref, w, h).copy_(gathered[r, k // self.world])
                 self.b.mark_result(ref, w, h)
+        self.b.sync()        # the scene's own stream must not run ahead of the collective's stream
+        self.wait_ms += 1e3 * (t1 - t0)
+        self.exchange_ms += 1e3 * (time.perf_counter() - t1)
 
-    def run(self):
+    def run(self, passes=range(4)):
         for i in range(self.rounds):
-            for pass_ in range(4):
+            for pass_ in passes:
                 self.run_pass(i, pass_)

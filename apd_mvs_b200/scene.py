@@ -150,12 +150,17 @@ def make_scene(W: int, H: int, n_src: int, seed: int = MASTER_SEED, device: str 
 
 
 def make_priors(scene: dict, seed: int = MASTER_SEED + 1, depth_noise: float = 0.01, normal_deg: float = 5.0,
-                views_mask: int = 0b1111):
+                views_mask: int = 0b1111, order=None):
     """Priors of a refinement pass (SURVEY §8d cfg 3): noisy GT depth/normal, WEAK on the textureless
-    rectangles, UNKNOWN on the 6-px border, STRONG elsewhere; noisy GT depth for the source views."""
+    rectangles, UNKNOWN on the 6-px border, STRONG elsewhere; noisy GT depth for the source views.
+    `order`: view indices [reference, src_1 .. src_S] of this problem inside scene["depth"] (default: all, in order);
+    order[0] must be the view scene["normal"] / scene["weak_mask"] were rendered for."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     H, W = scene["H"], scene["W"]
     depth = scene["depth"].cpu()
+    if order is not None:
+        assert order[0] == scene.get("ref_index", 0)
+        depth = depth[list(order)]
     nrm = scene["normal"].cpu()
     d0 = depth[0] * (1.0 + depth_noise * torch.randn((H, W), generator=g))
     pert = torch.randn((H, W, 3), generator=g) * math.tan(math.radians(normal_deg)) / math.sqrt(2.0)

@@ -99,6 +99,13 @@ int apd_set_seed(apd_handle h, uint64_t seed);
 /* Use fewer images than the handle was created for (problems of one scene have different numbers of source
  * views, main.cpp:36-46); images, cameras and depths must be set again afterwards. */
 int apd_set_num_images(apd_handle h, int num_images);
+/* Handle reuse across problems (the reference constructs and destroys one APD object per (view, pass), main.cpp:91-138;
+ * a caller that keeps the handle instead calls this between problems): forgets every input that was set, so that the
+ * preconditions of apd_run (cameras, images, depth maps, priors: APD.cpp:492-581) are checked against the NEW problem.
+ * Device buffers, streams, texture objects and tensor maps are kept. */
+int apd_reset_inputs(apd_handle h);
+/* Image count the handle was created for (upper bound of apd_set_num_images). */
+int apd_get_capacity(apd_handle h);
 
 /* cams[num_images]; index 0 is the reference view (APD.cpp:633-634). */
 int apd_set_cameras(apd_handle h, const apd_camera *cams);

@@ -44,8 +44,16 @@ int apd_fusion_set_view_planes(apd_fusion_handle f, int view, const uint8_t *bgr
                                const float *planes_xyzw, const uint8_t *states, const uint8_t *block);
 int apd_fusion_add_problem(apd_fusion_handle f, int ref_view, const int *src_views, int n_src);
 
-/* Fuses all problems in order. */
+/* Fuses all problems in order (RunFusion, the ETH variant: the only one main.cpp calls, main.cpp:219). */
 int apd_fusion_run(apd_fusion_handle f);
+/* The two Tanks-and-Temples variants the reference defines next to it: RunFusion_TAT_Intermediate (APD.cpp:979-1147:
+ * at least k of the sources within k x (0.25 px, 1/3500 relative depth, 3 deg x k + 4 deg), k = 2.., colour averaged over
+ * the agreeing sources) and RunFusion_TAT_advanced (APD.cpp:1149-1296: k x (0.25 px, 1/3000), reference colour). Both keep
+ * the reference's carry-over of a source's last measurement to later pixels (`diff` is not reset per pixel) and mark only the
+ * reference view's own pixels. Pixel states are not used by these variants. */
+#define APD_FUSION_TAT_INTERMEDIATE 1
+#define APD_FUSION_TAT_ADVANCED 2
+int apd_fusion_run_tat(apd_fusion_handle f, int variant);
 long long apd_fusion_num_points(apd_fusion_handle f);
 /* xyz: 3 floats per point; color: 3 floats per point (blue, green, red averages, PointList.color). Either may be NULL. */
 int apd_fusion_get_points(apd_fusion_handle f, float *xyz, float *color_bgr);

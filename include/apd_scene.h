@@ -49,7 +49,10 @@ int apd_scene_set_view(apd_scene_handle s, int view, const float *image, size_t 
  * Problems run in the order they are added. */
 int apd_scene_add_problem(apd_scene_handle s, int ref_view, const int *src_views, int n_src);
 
-/* ComputeRoundNum, main.cpp:72-88. */
+/* ComputeRoundNum, main.cpp:72-88: the image is halved until its larger side is <= 1000. That constant is a literal in the
+ * reference (main.cpp:81); apd_scene_set_round_limit replaces it for this scene (before the first pass), e.g. 1920 to run
+ * the single-round schedule BASELINE configs[3] describes at 1920x1080. Default 1000. */
+int apd_scene_set_round_limit(apd_scene_handle s, int max_size);
 int apd_scene_num_rounds(apd_scene_handle s);
 /* Image size of a round: scale_size = 2^(rounds-1-round), size = round(full * 1/scale_size) (APD.cpp:466-468). */
 int apd_scene_round_size(apd_scene_handle s, int round, int *width, int *height);

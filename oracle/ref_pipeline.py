@@ -23,9 +23,9 @@ WEAK, STRONG, UNKNOWN = 0, 1, 2
 f32 = np.float32
 
 
-def compute_round_num(W: int, H: int) -> int:
+def compute_round_num(W: int, H: int, limit: int = 1000) -> int:
     max_size, rounds = max(W, H), 1
-    while max_size > 1000:
+    while max_size > limit:
         max_size //= 2
         rounds += 1
     return rounds
@@ -122,7 +122,7 @@ class RefPipeline:
     """main() of the reference on in-memory views. `run_patchmatch(images, cams, params, depths, planes, views,
     states, seed) -> (planes[H,W,4], states[H,W], views[H,W])` executes APD::RunPatchMatch (oracle/_ref)."""
 
-    def __init__(self, images, cameras, pairs, make_params, run_patchmatch, seed: int = 1234567):
+    def __init__(self, images, cameras, pairs, make_params, run_patchmatch, seed: int = 1234567, round_limit: int = 1000):
         self.images = np.ascontiguousarray(images, dtype=f32)
         self.n_views, self.H, self.W = self.images.shape
         self.cameras = cameras.copy()
@@ -130,7 +130,7 @@ class RefPipeline:
         self.make_params = make_params
         self.run_patchmatch = run_patchmatch
         self.seed = seed
-        self.rounds = compute_round_num(self.W, self.H)
+        self.rounds = compute_round_num(self.W, self.H, round_limit)
         self.results = [None] * self.n_views       # dict(depth, normal, weak, views) = the four files of a view
         self._scaled_cache = {}
 

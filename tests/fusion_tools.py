@@ -48,17 +48,19 @@ def write_dense_folder(root, ids, bgr, cams, depths, normals, weaks):
         write_mat(os.path.join(out, "weak.bin"), weaks[k].astype(np.uint8))
 
 
-def run_reference_fusion(root, problems):
-    """problems: [(ref_image_id, [src_image_ids])]. Returns (xyz float32 [n,3], bgr uint8 [n,3]) read from APD/APD.ply."""
+def run_reference_fusion(root, problems, variant=0):
+    """problems: [(ref_image_id, [src_image_ids])]. Returns (xyz float32 [n,3], bgr uint8 [n,3]) read from APD/APD.ply.
+    variant 0 = RunFusion, 1 = RunFusion_TAT_Intermediate, 2 = RunFusion_TAT_advanced."""
     L = C.CDLL(REF_LIB)
     L.apdfusion_ref_run.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    L.apdfusion_ref_run_variant.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int]
     n = len(problems); ms = max(1, max(len(s) for _, s in problems))
     refs = (C.c_int * n)(*[r for r, _ in problems]); cnt = (C.c_int * n)(*[len(s) for _, s in problems])
     src = (C.c_int * (n * ms))()
     for i, (_, s) in enumerate(problems):
         for j, v in enumerate(s):
             src[i * ms + j] = v
-    assert L.apdfusion_ref_run(str(root).encode(), n, refs, cnt, src, ms) == 0
+    assert L.apdfusion_ref_run_variant(str(root).encode(), n, refs, cnt, src, ms, variant) == 0
     return read_ply(os.path.join(root, "APD", "APD.ply"))
 
 

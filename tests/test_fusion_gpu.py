@@ -26,14 +26,14 @@ def depth_maps(W, H, V, n_src):
     return images, cams, pairs, out
 
 
-def fuse_gpu(bgr, cams, pairs, depths, normals, states, blocks=None):
+def fuse_gpu(bgr, cams, pairs, depths, normals, states, blocks=None, variant="eth"):
     V, H, W = len(depths), depths[0].shape[0], depths[0].shape[1]
     fu = F.Fusion(V, W, H)
     for v in range(V):
         fu.SetView(v, bgr[v], cams[v], depths[v], normals[v], states[v], None if blocks is None else blocks[v])
     for r, s in pairs:
         fu.AddProblem(r, s)
-    xyz, col = fu.RunFusion()
+    xyz, col = fu.RunFusion(variant)
     return fu, xyz, col
 
 
@@ -47,12 +47,11 @@ def test_fusion_matches_reference(tmp_path, W, H, V, n_src):
     ref_xyz, ref_bgr = FT.run_reference_fusion(tmp_path, [(ids[r], [ids[s] for s in ss]) for r, ss in pairs])
     fu, xyz, col = fuse_gpu(bgr, cams, pairs, depths, normals, states)
     assert len(ref_xyz) > 0.3 * W * H
-    if len(xyz) == len(ref_xyz) and np.array_equal(xyz.view(np.uint32), ref_xyz.view(np.uint32)):
-        assert np.array_equal(col.astype(np.uint8), ref_bgr)          # ExportPointCloud truncates to uchar
-    else:   # count the points that are not common (acosf / expf last-bit threshold flips)
-        a = {x.tobytes() for x in xyz}; b = {x.tobytes() for x in ref_xyz}
-        diff = len(a ^ b)
-        assert diff <= max(2, int(1e-4 * len(ref_xyz))), f"{diff} of {len(ref_xyz)} points differ"
+    # pinned at zero differing points: same points, same order, same coordinates and colours (the fusion TU is compiled with
+    # IEEE arithmetic; on these inputs no acosf / expf value sits on a threshold, so glibc and CUDA agree everywhere)
+    assert len(xyz) == len(ref_xyz), f"{len(xyz)} vs {len(ref_xyz)} points"
+    assert np.array_equal(xyz.view(np.uint32), ref_xyz.view(np.uint32))
+    assert np.array_equal(col.astype(np.uint8), ref_bgr)          # ExportPointCloud truncates to uchar
     # the PLY writer produces the reference's file layout
     ply = tmp_path / "ours.ply"
     fu.ExportPointCloud(ply)
@@ -60,6 +59,25 @@ def test_fusion_matches_reference(tmp_path, W, H, V, n_src):
     assert np.array_equal(pxyz.view(np.uint32), xyz.view(np.uint32)) and np.array_equal(pbgr, col.astype(np.uint8))
     t = fu.Timing()
     assert t["gpu_ms"] > 0 and t["max_rounds"] >= 1
+    fu.close()
+
+
+@pytest.mark.skipif(not FT.ref_available(), reason="oracle/_ref/libapd_fusion_ref.so not built")
+@pytest.mark.parametrize("variant,code", [("tat_intermediate", 1), ("tat_advanced", 2)])
+def test_tanks_and_temples_variants_match_reference(tmp_path, variant, code):
+    """RunFusion_TAT_Intermediate / RunFusion_TAT_advanced (APD.cpp:979-1296), including the carry-over of a source's last
+    measurement to later pixels (`diff` is declared per view, not per pixel): same points, same order, same bits."""
+    W, H, V, n_src = 352, 264, 5, 4
+    images, cams, pairs, (depths, normals, states) = depth_maps(W, H, V, n_src)
+    bgr = FT.colour_images(images)
+    ids = [3 + 2 * v for v in range(V)]
+    FT.write_dense_folder(tmp_path, ids, bgr, cams, depths, normals, states)
+    ref_xyz, ref_bgr = FT.run_reference_fusion(tmp_path, [(ids[r], [ids[s] for s in ss]) for r, ss in pairs], variant=code)
+    fu, xyz, col = fuse_gpu(bgr, cams, pairs, depths, normals, states, variant=variant)
+    assert len(ref_xyz) > 0.05 * W * H, len(ref_xyz)
+    assert len(xyz) == len(ref_xyz), f"{len(xyz)} vs {len(ref_xyz)} points"
+    assert np.array_equal(xyz.view(np.uint32), ref_xyz.view(np.uint32))
+    assert np.array_equal(col.astype(np.uint8), ref_bgr)
     fu.close()
 
 

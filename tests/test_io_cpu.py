@@ -102,3 +102,55 @@ def test_generate_sample_list_drops_non_positive_scores(tmp_path):
 
 def test_format_index():
     assert IO.ToFormatIndex(7) == "00000007" and IO.ToFormatIndex(12345678) == "12345678"
+
+
+# ---- pinned against the reference's OWN file code (APD.cpp:3-92, compiled unmodified into oracle/_ref/libapd_fusion_ref.so)
+def _ref_io():
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libapd_fusion_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libapd_fusion_ref.so not built")
+    L = C.CDLL(path)
+    if not hasattr(L, "apdref_write_bin_mat"):
+        pytest.skip("oracle/_ref/libapd_fusion_ref.so predates the file-I/O wrappers")
+    L.apdref_write_bin_mat.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.apdref_read_bin_mat.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.apdref_read_camera.argtypes = [C.c_char_p, C.c_void_p]
+    return L, C
+
+
+@pytest.mark.parametrize("arr,code", [
+    (np.random.default_rng(10).random((37, 53)).astype(np.float32) * 9.0, 5),            # depths.dmb   CV_32FC1
+    (np.random.default_rng(11).standard_normal((37, 53, 3)).astype(np.float32), 21),      # normals.dmb  CV_32FC3
+    (np.random.default_rng(12).integers(0, 3, (37, 53)).astype(np.uint8), 0),             # weak.bin     CV_8UC1
+    (np.random.default_rng(13).integers(0, 2 ** 31 - 1, (37, 53)).astype(np.int32), 4),   # selected_views.bin CV_32SC1
+])
+def test_files_written_by_the_reference_are_read_back_and_vice_versa(tmp_path, arr, code):
+    L, C = _ref_io()
+    a = np.ascontiguousarray(arr)
+    # the reference's WriteBinMat -> this library's reader
+    p = tmp_path / "ref_written.dmb"
+    assert L.apdref_write_bin_mat(str(p).encode(), a.ctypes.data, a.shape[0], a.shape[1], code) == 0
+    back = IO.ReadBinMat(p)
+    assert back.dtype == a.dtype and back.shape == a.shape and np.array_equal(back.view(np.uint8), a.view(np.uint8))
+    # this library's writer -> the reference's ReadBinMat; and both writers produce the same bytes
+    q = tmp_path / "ours_written.dmb"
+    IO.WriteBinMat(q, a)
+    assert q.read_bytes() == p.read_bytes()
+    out = np.empty_like(a)
+    r, c, t = C.c_int(), C.c_int(), C.c_int()
+    assert L.apdref_read_bin_mat(str(q).encode(), out.ctypes.data, out.nbytes, C.byref(r), C.byref(c), C.byref(t)) == 0
+    assert (r.value, c.value, t.value) == (a.shape[0], a.shape[1], code) and np.array_equal(out.view(np.uint8), a.view(np.uint8))
+
+
+def test_camera_file_parsed_like_the_reference(tmp_path):
+    L, C = _ref_io()
+    p = tmp_path / "00000003_cam.txt"
+    p.write_text(CAM)
+    mine = IO.ReadCamera(p)
+    ref = np.zeros(1, dtype=mine.dtype)
+    assert L.apdref_read_camera(str(p).encode(), ref.ctypes.data) == 0
+    for f in ("K", "R", "t", "c"):
+        assert np.array_equal(np.asarray(mine[f]).view(np.uint32), np.asarray(ref[0][f]).view(np.uint32)), f
+    assert mine["depth_min"] == ref[0]["depth_min"] and mine["depth_max"] == ref[0]["depth_max"]

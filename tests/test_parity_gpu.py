@@ -143,6 +143,82 @@ def test_full_size_properties():
     apd.close()
 
 
+# ---- full-size live-oracle cases (size-dependent machinery - slab pool under 148 occupied SMs, `int center`
+# indexing, TMA boxes overhanging the padded image, the compacted WEAK lists - checked against the reference itself)
+BIG_CASES = [
+    # BASELINE configs[1] at full size: 3111x2074, 9 sources, all STRONG, 3 iterations
+    dict(W=3111, H=2074, S=9, iters=3),
+    # BASELINE configs[2] at quarter resolution: deformation ON + geometric term
+    dict(W=1555, H=1036, S=9, iters=3, state=E.REFINE_ITER, geom=True, use_apd=True, rotate_time=4, ransac_threshold=0.00625, weak_peak_radius=4),
+]
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libapd_ref.so not built")
+@pytest.mark.parametrize("kw", BIG_CASES, ids=lambda k: f"{k['W']}x{k['H']}-S{k['S']}-state{k.get('state', 0)}")
+def test_full_size_live_reference_bit_exact(kw):
+    kw = dict(kw)
+    case = T.build_case(kw.pop("W"), kw.pop("H"), kw.pop("S"), device="cuda", **kw)
+    d = T.final_diff(case, 1234567)
+    assert all(v == 0.0 for v in d.values()), d
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libapd_ref.so not built")
+def test_cfg4_shape_both_passes_bit_exact():
+    """BASELINE configs[3] shape: 1920x1080, 10 sources; the FIRST_INIT pass, then a REFINE_ITER + geometric pass fed
+    with the first pass's own outputs (planes, selected views, pixel states) as ProcessProblem / InuputInitialization
+    hand them over (main.cpp:105-124, APD.cpp:492-581). Both passes against the reference on identical inputs."""
+    W, H, S = 1920, 1080, 10
+    case = T.build_case(W, H, S, iters=3, device="cuda")
+    ref = T.make_reference(case); ref.run(); rp, rs, rv = ref.outputs(); ref.close()
+    apd = T.make_product(case); apd.RunPatchMatch()
+    mp, ms, mv = apd.GetPlaneHypotheses(), apd.GetPixelStates(), apd.GetSelectedViews()
+    apd.close()
+    assert np.array_equal(bits(mp), bits(rp)) and np.array_equal(ms, rs) and np.array_equal(mv, rv)
+    # second pass: priors = first pass results after the depth-range test of main.cpp:109-112; depth maps of the
+    # source views = the scene's exact depths (what the other problems of the pass would have written)
+    planes = mp.copy(); states = ms.copy()
+    dmin, dmax = np.float32(case["cameras"][0]["depth_min"]) * np.float32(0.6), np.float32(case["cameras"][0]["depth_max"]) * np.float32(1.2)
+    bad = (planes[..., 3] < dmin) | (planes[..., 3] > dmax)
+    planes[bad, 3] = 0; states[bad] = E.UNKNOWN
+    depths = case["scene"]["depth"].cpu().numpy().copy()
+    depths[0] = planes[..., 3]
+    case2 = dict(case)
+    case2["params"] = E.default_params(max_iterations=3, state=E.REFINE_ITER, use_APD=0, geom_consistency=1, weak_peak_radius=4)
+    case2.update(planes=planes, views=mv, states=None, depths=depths)
+    d = T.final_diff(case2, 7654321)
+    assert all(v == 0.0 for v in d.values()), d
+    # and with the deformation path switched on for the pass (the weak map of pass 1 selects the WEAK pixels)
+    case3 = dict(case2)
+    case3["params"] = E.default_params(max_iterations=3, state=E.REFINE_ITER, use_APD=1, geom_consistency=1, weak_peak_radius=4,
+                                       rotate_time=2, ransac_threshold=0.00875)
+    case3["states"] = states
+    d = T.final_diff(case3, 7654321)
+    assert all(v == 0.0 for v in d.values()), d
+
+
+def test_rerun_after_other_inputs_is_clean():
+    """One handle, two different problems in a row, then the first again (what the scene layer does with its per-round
+    engine): no state of the previous run may leak (view weights and costs are reset per run)."""
+    a = T.build_case(129, 97, 3, iters=1, device="cuda", state=E.REFINE_ITER, geom=True, use_apd=True)       # H odd: rows >= half_rows untouched
+    apd = T.make_product(a)
+    apd.RunPatchMatch(); first = T.product_state(apd)
+    p1 = T.clone_params(apd.problem.params)          # incl. the depth range InuputInitialization derived (APD.cpp:454-455)
+    p2 = T.clone_params(p1); p2.max_iterations = 2
+    apd.SetParams(p2); apd.RunPatchMatch()
+    apd.SetParams(p1); apd.RunPatchMatch(); again = T.product_state(apd)
+    assert max(T.diff_state(first, again).values()) == 0.0
+    apd.close()
+
+
+def test_weak_peak_radius_limit():
+    case = T.build_case(64, 48, 2, device="cuda")
+    p = T.clone_params(case["params"]); p.weak_peak_radius = 29
+    apd = E.APD(E.Problem(case["images"], case["cameras"], p))
+    apd.InuputInitialization()
+    with pytest.raises(E.ApdError):
+        apd.CudaSpaceInitialization()
+
+
 def test_error_behaviour_matches_reference_preconditions():
     case = T.build_case(64, 48, 2, device="cuda")
     p = T.clone_params(case["params"]); p.geom_consistency = 1

@@ -95,6 +95,25 @@ def test_whole_pipeline_bit_exact(W, H, n_views, n_src):
     sc.close()
 
 
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref/libapd_ref.so not built")
+def test_unequal_source_counts_smaller_first():
+    """pair.txt drops sources with score <= 0 (main.cpp:42-44), so problems of one round have different numbers of
+    images. The depth-map array of the round's engine is created lazily by the first geometric problem: it must hold the
+    round's maximum, not that problem's count (apd_engine.cu make_layered)."""
+    images, cams = make_views(600, 448, 4)
+    pairs = [(0, [1]), (1, [2, 3, 0]), (2, [3, 0]), (3, [0, 1, 2])]
+    ref = RP.RefPipeline(images, cams, pairs, E.default_params, run_reference_patchmatch, seed=99)
+    sc = P.Scene(images, cams, pairs, seed=99)
+    for ps in range(4):
+        ref.run_pass(0, ps)
+        sc.RunPass(0, ps)
+    for v in range(4):
+        r = ref.results[v]
+        assert np.array_equal(bits(sc.Depth(v)), bits(r["depth"])), v
+        assert np.array_equal(sc.States(v), r["weak"]) and np.array_equal(sc.SelectedViews(v), r["views"]), v
+    sc.close()
+
+
 def test_run_equals_pass_by_pass():
     images, cams = make_views(1000, 512, 3)            # one round (max size <= 1000)
     pairs = P.ring_pairs(3, 2)

@@ -35,7 +35,7 @@ def main():
         a, b = os.path.join(d, "ref"), os.path.join(d, "ours")
         TM.write_inputs(a, list(range(V)), bgr, sc["cameras"], pairs); TM.write_inputs(b, list(range(V)), bgr, sc["cameras"], pairs)
         t0 = time.perf_counter(); r1 = subprocess.run([TM.REF_EXE, a, "0"], capture_output=True, text=True)
-        t1 = time.perf_counter(); r2 = subprocess.run([TM.OUR_EXE, b, "0"], capture_output=True, text=True, env=dict(os.environ, APD_SEED="1234567"))
+        t1 = time.perf_counter(); r2 = subprocess.run([TM.OUR_EXE, b, "0"], capture_output=True, text=True, env=dict(os.environ, APD_SEED="1234567", APD_B200_TIMING="1"))
         t2 = time.perf_counter()
         assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr[-500:], r2.stderr[-500:])
         same = open(os.path.join(a, "APD", "APD.ply"), "rb").read() == open(os.path.join(b, "APD", "APD.ply"), "rb").read()
@@ -46,7 +46,10 @@ def main():
         line = {"workload": f"{V} views {W}x{H}, {S} source views each, 1 round x 4 passes = {4 * V} ProcessProblem calls + RunFusion (CPU)",
                 "reference_program_s": round(t1 - t0, 2), "facade_build_s": round(t2 - t1, 2),
                 "reference_sum_ProcessProblem_ms": cost_ms(r1.stdout), "facade_sum_ProcessProblem_ms": cost_ms(r2.stdout),
-                "fused_points": n, "ply_byte_identical": bool(same)}
+                "fused_points": n, "ply_byte_identical": bool(same),
+                "facade_own_time": next((l for l in r2.stderr.splitlines() if l.startswith("[apd_b200 facade]")), None)}
+        if os.environ.get("APD_B200_POOL") == "0":
+            line["pool"] = "off"
     print(json.dumps(line))
     if args.out:
         json.dump(line, open(args.out, "w"), indent=1)
