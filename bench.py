@@ -483,7 +483,16 @@ def main():
     # ---- max over ranks
     vals = torch.tensor([res["iter_ms"], res["dev_step_ms"], res["e2e_ms"], res["total_ms"], res.get("e2e_lifecycle_ms", 0.0)]
                         + [res["kernel_ms"][k] for k in ("k_strong", "k_weak", "k_sweep")], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1 and args.impl == "ours":
+        # what every rank measured on ITS reference view: the units differ (each view has its own share of WEAK pixels), so
+        # max-over-ranks timing includes that imbalance; there is no communication inside a step
+        n_weak = float((case["states"] == 0).sum()) if case.get("states") is not None else 0.0
+        mine = torch.tensor([res["iter_ms"], res["dev_step_ms"], res["kernel_ms"]["k_weak"], n_weak], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"iter_ms": [round(float(t[0]), 3) for t in allr], "ms_per_step": [round(float(t[1]), 3) for t in allr],
+                    "k_weak_ms": [round(float(t[2]), 3) for t in allr], "weak_pixels": [int(t[3]) for t in allr]}
         shard.max_over_ranks(vals)
     iter_ms, dev_step_ms, e2e_ms, total_ms, life_ms, ms_strong, ms_weak, ms_sweep = [float(v) for v in vals.tolist()]
     n_units = world if args.impl == "ours" else 1
@@ -578,6 +587,10 @@ def main():
             line["e2e"]["outputs_equal_device_path"] = res.get("e2e_crc_equal")
         if world > 1:
             line["setup_broadcast_ms"] = round(res["bcast_ms"], 2)
+            if per_rank:
+                line["per_rank"] = per_rank
+                line["per_rank"]["note"] = ("one reference view per rank, no collective inside a step; `value` uses the slowest rank, whose view simply holds more "
+                                            "WEAK pixels - the spread below is input imbalance, not communication")
         if args.impl == "reference":
             line["cpu_baseline"] = {"value": round(value, 2), "unit": "Mpixels*views/s", "cores": 1, "kind": "reference",
                                     "sample": "whole workload; the reference has no CPU path: its CUDA build (sm_100 recompile) on 1 GPU, host side single-threaded"}

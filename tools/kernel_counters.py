@@ -10,6 +10,7 @@ import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, workload = sys.argv[1], sys.argv[2]
 desc = sys.argv[3] if len(sys.argv) > 3 else f"ncu capture {os.path.basename(rep)}"
+MERGE = True        # several reports (one kernel each) may be folded into one workload entry
 KERNELS = {"k_strong": "k_strong", "k_weak": "k_weak_q", "k_sweep": "k_sweep"}
 
 
@@ -80,6 +81,6 @@ for key, pat in KERNELS.items():
     out[key] = ent
 path = os.path.join(ROOT, "profiles", "kernel_counters.json")
 allc = json.load(open(path)) if os.path.exists(path) else {}
-allc[workload] = out
+allc.setdefault(workload, {}).update(out)
 json.dump(allc, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))

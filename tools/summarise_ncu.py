@@ -97,7 +97,7 @@ def main():
     json.dump(out, open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.json"), "w"), indent=1)
     # traffic of the dominant kernel (mean over its captured launches)
     tr = [k["dram_bytes_per_launch"] for k in out["kernels"] if "k_strong" in k["name"] and k.get("dram_bytes_per_launch")]
-    if tr:
+    if tr and tag.startswith("r01"):        # round 1 file layout; round 2: tools/kernel_counters.py -> profiles/kernel_counters.json
         json.dump({"kernel": "k_strong", "workload": "cfg2", "dram_bytes_per_launch": sum(tr) / len(tr), "launches_captured": len(tr),
                    "source": f"profiles/{tag}_ncu_summary.json"}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     # launch list
