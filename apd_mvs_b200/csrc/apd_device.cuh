@@ -435,14 +435,22 @@ __device__ __forceinline__ void slab_exit(const Args &a, int *s_slot, int nthrea
 	if (atomicAdd(&s_slot[1], 1) == nthreads - 1) atomicExch(&a.slab_slots[s_slot[0]], 0);
 }
 
-// ComputeGeomConsistencyCost, APD.cu:752-789
-__device__ __forceinline__ float geom_cost(const Args &a, const RefConst &rc, const ViewConst &vc, int layer, const float4 pl, float xf, float yf) {
+// ComputeGeomConsistencyCost, APD.cu:752-789, in two pieces: the world point of the pixel at the hypothesis' depth does not
+// depend on the source view (APD.cu:758-764), so callers that visit several views with one plane compute it once.
+struct GeomPoint { float x, y, z; };
+__device__ __forceinline__ GeomPoint geom_point(const RefConst &rc, const float4 pl, float xf, float yf) {
 	const float depth = plane_depth(rc, pl, xf, yf);
 	float X0, X1; backproject(rc, xf, yf, depth, X0, X1);
 	const float *R = rc.cam.R;
-	float Px = rc.cam.c[0] + fmaf(R[6], depth, fmaf(R[0], X0, R[3] * X1));
-	float Py = rc.cam.c[1] + fmaf(R[7], depth, fmaf(R[1], X0, R[4] * X1));
-	float Pz = rc.cam.c[2] + fmaf(R[8], depth, fmaf(R[2], X0, R[5] * X1));
+	GeomPoint P;
+	P.x = rc.cam.c[0] + fmaf(R[6], depth, fmaf(R[0], X0, R[3] * X1));
+	P.y = rc.cam.c[1] + fmaf(R[7], depth, fmaf(R[1], X0, R[4] * X1));
+	P.z = rc.cam.c[2] + fmaf(R[8], depth, fmaf(R[2], X0, R[5] * X1));
+	return P;
+}
+__device__ __forceinline__ float geom_cost_at(const Args &a, const RefConst &rc, const ViewConst &vc, int layer, const GeomPoint P, float xf, float yf) {
+	const float *R = rc.cam.R;
+	const float Px = P.x, Py = P.y, Pz = P.z;
 	const apd_camera &s = vc.cam;
 	float tx = s.t[0] + fmaf(s.R[2], Pz, fmaf(s.R[0], Px, s.R[1] * Py));
 	float ty = s.t[1] + fmaf(s.R[5], Pz, fmaf(s.R[3], Px, s.R[4] * Py));
@@ -466,6 +474,9 @@ __device__ __forceinline__ float geom_cost(const Args &a, const RefConst &rc, co
 	float dc = fmaf(-fmaf(K[2], uz, fmaf(K[0], ux, K[1] * uy)), rb, xf);
 	float dr = fmaf(-fmaf(K[5], uz, fmaf(K[3], ux, K[4] * uy)), rb, yf);
 	return fminf(sqrtaf(fmaf(dc, dc, dr * dr)), 3.0f);
+}
+__device__ __forceinline__ float geom_cost(const Args &a, const RefConst &rc, const ViewConst &vc, int layer, const float4 pl, float xf, float yf) {
+	return geom_cost_at(a, rc, vc, layer, geom_point(rc, pl, xf, yf), xf, yf);
 }
 
 // view weights: 32 nibbles (sum <= 15) in one uint4 per pixel (reference: 32 bytes, APD.cpp:645)

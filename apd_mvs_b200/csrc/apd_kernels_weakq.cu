@@ -551,9 +551,10 @@ __global__ void __launch_bounds__(kWqNT, MINB) k_weak_q(const Args a, const int 
 				CM(ql, v0) = cand0 ? c0 : ((ql == 0 && v0 == 0) ? 2.0f : 0.0f);
 				CM(ql + 4, v0) = cand1 ? c1 : 0.0f;
 			} else if (phase == 1) {
-				if (a.geom) {
-					if (s0) c0 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v0], v0 + 1, T, xf, yf), c0);
-					if (s1) c1 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v1], v1 + 1, T, xf, yf), c1);
+				if (a.geom) {      // both slots hold the same plane: its world point is computed once (geom_point)
+					const GeomPoint gp = geom_point(rc, T, xf, yf);
+					if (s0) c0 = fmaf(a.geom_factor, geom_cost_at(a, rc, sv[v0], v0 + 1, gp, xf, yf), c0);
+					if (s1) c1 = fmaf(a.geom_factor, geom_cost_at(a, rc, sv[v1], v1 + 1, gp, xf, yf), c1);
 				}
 				// the four views of this step in ascending order: position p sits in slot p>>1 of lane pair p&1
 #pragma unroll
@@ -568,13 +569,15 @@ __global__ void __launch_bounds__(kWqNT, MINB) k_weak_q(const Args a, const int 
 					}
 				}
 			} else if (phase == 2) {
+				GeomPoint gp; gp.x = gp.y = gp.z = 0.f;
+				if (a.geom && s0) gp = geom_point(rc, T, xf, yf);
 				if (s0) {
-					if (a.geom) c0 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v0], v0 + 1, T, xf, yf), c0);
+					if (a.geom) c0 = fmaf(a.geom_factor, geom_cost_at(a, rc, sv[v0], v0 + 1, gp, xf, yf), c0);
 					my_acc = fmaf((float)vw_get(vw, v0), c0, my_acc);
 					if (prune && my_acc * inv_wn >= limit) my_busy = false;
 				}
 				if (s1 && my_busy) {
-					if (a.geom) c1 = fmaf(a.geom_factor, geom_cost(a, rc, sv[v1], v1 + 1, T, xf, yf), c1);
+					if (a.geom) c1 = fmaf(a.geom_factor, geom_cost_at(a, rc, sv[v1], v1 + 1, gp, xf, yf), c1);
 					my_acc = fmaf((float)vw_get(vw, v1), c1, my_acc);
 					if (prune && my_acc * inv_wn >= limit) my_busy = false;
 				}
