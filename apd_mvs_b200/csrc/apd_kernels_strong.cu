@@ -688,8 +688,6 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 		float4 t = c.pl;
 		t.w = plane_offset(rc, xf, yf, d, t.x, t.y, t.z);
 		float acc14 = 0.0f, acc15 = 0.0f;
-		GeomPoint gp; gp.x = gp.y = gp.z = 0.0f;
-		if (a.geom) gp = geom_point(rc, t, xf, yf);          // the same for every view of this step
 		// per-lane list of the views that count: selected AND sampled (a zero weight multiplies the cost by 0 in
 		// the reference); ascending order = the reference's summation order
 		uint32_t m = need ? act : 0u;
@@ -703,7 +701,7 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 			ncc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
 			if (want) {
 				float g = 0.0f;
-				if (a.geom) g = geom_cost_at(a, rc, sv[v], v + 1, gp, xf, yf);
+				if (a.geom) g = geom_cost(a, rc, sv[v], v + 1, t, xf, yf);       // hoisting its view-independent half (geom_point) costs registers: 372 vs 368 ms at cfg3
 				if (DO14) acc14 = fmaf((float)w, a.geom ? fmaf(a.geom_factor, g, ncc) : ncc, acc14);          // APD.cu:2074-2078
 				if (DO15) { acc15 = fmaf((float)w, ncc, acc15); if (a.geom) acc15 = fmaf((float)w, a.geom_factor * g, acc15); }   // :2217-2220
 			}
@@ -742,8 +740,6 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 		float4 t = c.pl;
 		{ float X0, X1; backproject(rc, xf, yf, c.depth, X0, X1); t.w = -((c.depth * t.z) + fmaf(X0, t.x, X1 * t.y)); }
 		float cost_sum = 0.0f;
-		GeomPoint gp; gp.x = gp.y = gp.z = 0.0f;
-		if (a.geom) gp = geom_point(rc, t, xf, yf);
 		uint32_t m = on15 ? act : 0u;
 #pragma unroll 1
 		while (__any_sync(0xffffffffu, m != 0u)) {
@@ -754,7 +750,7 @@ __global__ void __launch_bounds__(kSweepNT, 4) k_sweep(const Args a, const __gri
 			float tc = kCostMax;
 			tc = ncc6_quad<4, false>(qc, a.img_tex, v + 1, make_homography(rc, sv[v], t), sv[v], want, tile, C::PW, lx, ly, px, py, inv36);
 			if (want) {
-				if (a.geom) tc = fmaf(a.geom_factor, geom_cost_at(a, rc, sv[v], v + 1, gp, xf, yf), tc);
+				if (a.geom) tc = fmaf(a.geom_factor, geom_cost(a, rc, sv[v], v + 1, t, xf, yf), tc);
 				cost_sum = fmaf((float)w, tc, cost_sum);
 			}
 		}

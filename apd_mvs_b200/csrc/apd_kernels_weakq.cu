@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kWqNT, MINB) k_weak_q(const Args a, const int 
 		Refine5 rf; rf.depth_rand = rf.depth_pert = rf.d0 = 0.f; rf.n_rand = rf.n_pert = rf.n0 = pl_now;
 
 #pragma unroll 1
-		for (int step = 0; step < 3 * S + 16; ++step) {
+		for (int step = 0; step < 4 * S + 16; ++step) {      // S matrix steps + at most S/4 + 2S + a few (never reached)
 			// ---- phase transitions (quad-uniform; quads of a warp may be in different phases)
 #pragma unroll 1
 			while (phase < 3 && ((phase < 2) ? (m == 0u) : (q_busy == 0u && !pending2))) {

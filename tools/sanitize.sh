@@ -31,6 +31,9 @@ for r, ss in P.ring_pairs(3, 2):
     fu.AddProblem(r, ss)
 xyz, col = fu.RunFusion()
 print("fusion", len(xyz), fu.Timing()["max_rounds"])
+for variant in ("tat_intermediate", "tat_advanced"):
+    xyz, col = fu.RunFusion(variant)
+    print("fusion", variant, len(xyz))
 fu.close()
 s.close()
 PY
