@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <curand_kernel.h>
 #include "apd_device.cuh"
 
 namespace apd {
@@ -102,9 +103,17 @@ __device__ __forceinline__ float plane_dist(const float4 pl, const float3 p) {
 // constant, 0 = read it at run time. The kernel is ALU bound (ncu: 76 % of the ALU pipe, profiles/r02_*), so:
 //  * `% shift_range` becomes a multiply-shift;
 //  * with RANGE == 1 the jitter is always 0, the four tries of a radius test the SAME candidate against read-only
-//    data, so it is tested once; the generator still advances by the 4 (success at the first try) or 16 draws the
-//    reference consumes.
-__device__ __forceinline__ void rng_skip(Rng &r, int n) { for (int i = 0; i < n; ++i) (void)rng_next(r); }
+//    data, so it is tested once; the draws the reference consumes (4 on success at the first try, else 16) are only
+//    COUNTED during the search - their values are never read - and the generator jumps ahead once, before the RANSAC.
+// Advance the generator by n draws whose values nobody reads: cuRAND's own jump-ahead (precomputed matrices of the XORWOW
+// recurrence for 4^k steps, curand_kernel.h `skipahead`) - a dozen 160x160-bit matrix-vector products for the ~18 000 draws
+// a pixel's search consumes at 6221x4146, instead of 18 000 generator steps.
+__device__ __forceinline__ void rng_skipahead(Rng &r, unsigned int n) {
+	curandStateXORWOW_t st;
+	st.v[0] = r.v0; st.v[1] = r.v1; st.v[2] = r.v2; st.v[3] = r.v3; st.v[4] = r.v4; st.d = r.d;
+	skipahead((unsigned long long)n, &st);
+	r.v0 = st.v[0]; r.v1 = st.v[1]; r.v2 = st.v[2]; r.v3 = st.v[3]; r.v4 = st.v[4]; r.d = st.d;
+}
 
 template <int RANGE>
 __global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorConsts *acp) {
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorC
 	a.anchors[center] = make_short2((short)px, (short)py);
 	Rng rng = rng_load(a.rng, center);
 	short2 sp[32]; unsigned valid = 0u; int found = 0;
+	unsigned int skipped = 0u;           // RANGE == 1: draws consumed by the search so far
 	for (int i = 0; i < 32; ++i) sp[i] = make_short2(-1, -1);
 	const float pxf = (float)px, pyf = (float)py, Wf = (float)W, Hf = (float)H;
 	const unsigned range = RANGE ? (unsigned)RANGE : (unsigned)ac.shift_range;
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorC
 							hit = cosv > ac.thresh;
 						}
 					}
-					if (RANGE == 1) rng_skip(rng, hit ? 4 : 16);     // first try succeeds, or all four fail alike
+					if (RANGE == 1) skipped += hit ? 4u : 16u;      // first try succeeds, or all four fail alike
 					if (hit) { sp[di] = make_short2((short)nx, (short)ny); valid |= 1u << di; ++found; break; }
 				}
 				if ((valid >> di) & 1u) break;
@@ -178,6 +188,7 @@ __global__ void __launch_bounds__(128) k_gen_anchors(const Args a, const AnchorC
 			normalize2(dx, dy);
 		}
 	}
+	if (RANGE == 1) rng_skipahead(rng, skipped);
 	if (found <= 3) { a.reliable[center] = 0; rng_store(a.rng, center, rng); return; }
 
 	short2 pts[32]; float3 p3[32]; int vc = 0;
