@@ -493,4 +493,24 @@ __device__ __forceinline__ uint32_t vw_mask(const VW &w, int S) {
 	return m;
 }
 
+// Shared front end of K14 and K15: plane back into the reference camera frame, mean baseline and
+// summed weights over the selected views (APD.cu:2012-2052, :2160-2199).
+struct SweepCtx { float4 pl; float depth, weight_normal, kb, disp; int valid; };
+__device__ __forceinline__ bool sweep_setup(const Args &a, const RefConst &rc, const ViewConst *sv, size_t center, uint32_t bits, const VW &vw, SweepCtx &c) {
+	const float4 in = a.planes[center];
+	const float *R = rc.cam.R;
+	c.pl.x = fmaf(in.z, R[2], fmaf(in.x, R[0], in.y * R[1]));
+	c.pl.y = fmaf(in.z, R[5], fmaf(in.x, R[3], in.y * R[4]));
+	c.pl.z = fmaf(in.z, R[8], fmaf(in.x, R[6], in.y * R[7]));
+	c.pl.w = in.w; c.depth = in.w;
+	if (c.depth == 0.0f) return false;
+	float base = 0.0f; c.weight_normal = 0.0f; c.valid = 0;
+	for (int v = 0; v < a.S; ++v) if ((bits >> v) & 1u) { base += sv[v].baseline; c.weight_normal += (float)vw_get(vw, v); c.valid++; }
+	if (c.valid == 0) return true;
+	base = rcpf((float)c.valid) * base;
+	c.kb = base * rc.cam.K[0];
+	c.disp = c.kb * rcpf(c.depth);
+	return true;
+}
+
 }  // namespace apd

@@ -34,6 +34,7 @@ cudaError_t launch_weak(cudaStream_t, const Args &, int iter, int color);
 // quad-per-pixel WEAK propagation over compacted lists (apd_kernels_weakq.cu)
 cudaError_t launch_weak_lists(cudaStream_t, const Args &, bool split);
 cudaError_t launch_weak_q(cudaStream_t, const Args &, int iter, int color, int work_slot, int num_sms);
+cudaError_t launch_sweep_q(cudaStream_t, const Args &, int mode, int num_sms);
 }  // namespace apd
 
 using namespace apd;
@@ -130,6 +131,8 @@ extern "C" int apd_create(apd_handle *out, int device, int width, int height, in
 		h->num_sms = sms;
 		const char *w = getenv("APD_WEAK_IMPL");
 		h->weak_impl = (w && !strcmp(w, "old")) ? 0 : 1;
+		const char *sw = getenv("APD_SWEEP_IMPL");
+		h->sweep_impl = (sw && !strcmp(sw, "old")) ? 0 : 1;
 	}
 #undef ALLOC
 	if (make_layered(h, &h->img_arr, &h->img_tex) != APD_OK) return bail(APD_E_CUDA);
@@ -355,8 +358,8 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	launch_median(st, a, 0); h->launches++; STAGE_END();                                                   // K12
 	launch_median(st, a, 1); h->launches++; STAGE_END();                                                   // K13
 	// K14 and K15 are one fused launch (reported in the K14 slot) unless the run stops between them
-	if (stage_end == stage) { CKH(launch_sweep(st, a, 0, &h->tmap_sweep)); h->launches++; STAGE_END(); }                   // K14 alone
-	CKH(launch_sweep(st, a, 2, &h->tmap_sweep)); h->launches++; STAGE_END();                                               // K14 + K15
+	if (stage_end == stage) { CKH(h->sweep_impl == 1 ? launch_sweep_q(st, a, 0, h->num_sms) : launch_sweep(st, a, 0, &h->tmap_sweep)); h->launches++; STAGE_END(); }   // K14 alone
+	CKH(h->sweep_impl == 1 ? launch_sweep_q(st, a, 2, h->num_sms) : launch_sweep(st, a, 2, &h->tmap_sweep)); h->launches++; STAGE_END();                                 // K14 + K15
 	STAGE_END();
 #undef STAGE_END
 done:

@@ -30,6 +30,7 @@ struct apd_engine {
 	void *anchor_consts = nullptr;                                     // K3's rotation constants, one set per handle
 	int num_sms = 0;
 	int weak_impl = 1;                                                 // 1 = quad-per-pixel k_weak_q, 0 = first design (APD_WEAK_IMPL=old)
+	int sweep_impl = 1;                                                // 1 = quad-per-pixel k_sweep_q, 0 = first design (APD_SWEEP_IMPL=old)
 	CUtensorMap tmap_strong, tmap_sweep;
 	bool have_images = false, have_cams = false, have_depths = false, have_planes = false, have_states = false;
 	std::vector<cudaEvent_t> events;

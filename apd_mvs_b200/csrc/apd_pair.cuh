@@ -1,0 +1,121 @@
+// Two evaluations per lane, computed as packed fp32 pairs: shared by the quad-per-pixel kernels (k_weak_q, k_sweep_q).
+#pragma once
+#include "apd_device.cuh"
+
+namespace apd {
+
+// ---- two evaluations per lane ("slots" 0 and 1), computed as packed fp32 pairs ---------------------------------------
+// A lane always carries two evaluations through the deformable NCC: two candidate planes against one view (cost matrix),
+// one plane against two views (current / fit / refinement hypotheses). Both slots execute the same operations on
+// different data, so every FMUL/FADD/FFMA of the evaluation is issued ONCE as an f32x2 instruction (lo = slot 0,
+// hi = slot 1; same IEEE roundings as the scalar forms, apd_device.cuh), which halves the issue slots of a kernel that ncu
+// showed to be issue bound once its fetches were compact (profiles/r02w_*).
+struct Homog2 { f32x2 h[9]; };
+
+// make_homography (apd_device.cuh) for both slots. Negations are moved onto an operand: -(a*b) == (-a)*b exactly.
+__device__ __forceinline__ Homog2 make_homography2(const RefConst &rc, const ViewConst &v0, const ViewConst &v1, const float4 p0, const float4 p1) {
+	const f32x2 RW = pk2(rcpf(p0.w), rcpf(p1.w));
+	const f32x2 NX = pk2(-p0.x, -p1.x), NY = pk2(-p0.y, -p1.y), NZ = pk2(-p0.z, -p1.z);
+	f32x2 H[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		const f32x2 t = pk2(v0.trel[r], v1.trel[r]);
+		H[3 * r + 0] = fma2(mul2(NX, t), RW, pk2(v0.Rrel[3 * r + 0], v1.Rrel[3 * r + 0]));
+		H[3 * r + 1] = fma2(mul2(NY, t), RW, pk2(v0.Rrel[3 * r + 1], v1.Rrel[3 * r + 1]));
+		H[3 * r + 2] = fma2(mul2(NZ, t), RW, pk2(v0.Rrel[3 * r + 2], v1.Rrel[3 * r + 2]));
+	}
+	const f32x2 rK0 = pk2(rc.rK0, rc.rK0), rK4 = pk2(rc.rK4, rc.rK4);
+	const f32x2 nK2 = pk2(-rc.cam.K[2], -rc.cam.K[2]), nK5 = pk2(-rc.cam.K[5], -rc.cam.K[5]);
+	f32x2 T[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		T[3 * r + 0] = mul2(H[3 * r + 0], rK0);
+		T[3 * r + 1] = mul2(H[3 * r + 1], rK4);
+		T[3 * r + 2] = add2(H[3 * r + 2], fma2(mul2(nK2, H[3 * r + 0]), rK0, mul2(mul2(nK5, H[3 * r + 1]), rK4)));
+	}
+	const f32x2 K0 = pk2(v0.K0, v1.K0), K2 = pk2(v0.K2, v1.K2), K4 = pk2(v0.K4, v1.K4), K5 = pk2(v0.K5, v1.K5), K8 = pk2(v0.K8, v1.K8);
+	Homog2 o;
+	o.h[0] = fma2(K0, T[0], mul2(K2, T[6]));
+	o.h[1] = fma2(K0, T[1], mul2(K2, T[7]));
+	o.h[2] = fma2(K0, T[2], mul2(K2, T[8]));
+	o.h[3] = fma2(K4, T[3], mul2(K5, T[6]));
+	o.h[4] = fma2(K4, T[4], mul2(K5, T[7]));
+	o.h[5] = fma2(K4, T[5], mul2(K5, T[8]));
+	o.h[6] = mul2(K8, T[6]);
+	o.h[7] = mul2(K8, T[7]);
+	o.h[8] = mul2(K8, T[8]);
+	return o;
+}
+// (H (x, y, 1))_xy / z for both slots: ComputeCorrespondingPoint as inlined at APD.cu:426-432 and :545
+__device__ __forceinline__ void project2(const Homog2 &H, float xf, float yf, float &x0, float &y0, float &x1, float &y1) {
+	const f32x2 XF = pk2(xf, xf), YF = pk2(yf, yf);
+	const f32x2 Z = add2(H.h[8], fma2(H.h[6], XF, mul2(H.h[7], YF)));
+	float z0, z1; unpk2(Z, z0, z1);
+	const f32x2 RZ = pk2(rcpf(z0), rcpf(z1));
+	const f32x2 X = mul2(add2(H.h[2], fma2(H.h[0], XF, mul2(H.h[1], YF))), RZ);
+	const f32x2 Y = mul2(add2(H.h[5], fma2(H.h[3], XF, mul2(H.h[4], YF))), RZ);
+	unpk2(X, x0, x1); unpk2(Y, y0, y1);
+}
+
+// NCC of one window for the two slots of this lane (same reference taps; APD.cu:456-505 / :556-610)
+// `col`: the window's reference taps in evaluation order, STRIDE floats apart (a per-pixel shared-memory column)
+template <int INC, int STRIDE>
+__device__ __forceinline__ void wq_window2(cudaTextureObject_t tex, int lay0, int lay1, const Homog2 &H, bool w0, bool w1,
+                                           int cx, int cy, float inv_w, const float *col, float sum_r, float sum_rr, float &o0, float &o1) {
+	f32x2 TS = 0ull, TSS = 0ull, TRS = 0ull;
+	const float cxf = (float)cx, cyf = (float)cy;         // tap coordinates are small integers: cxf + i == (float)(cx + i) exactly
+	int n = 0;
+#pragma unroll(INC == 5 ? 3 : 1)
+	for (int i = -5; i <= 5; i += INC) {
+		const float xf = cxf + (float)i;
+		const f32x2 XF = pk2(xf, xf);
+		const f32x2 AX = mul2(H.h[0], XF), AY = mul2(H.h[3], XF), AZ = mul2(H.h[6], XF);
+		f32x2 RS = 0ull, S = 0ull, SS = 0ull;
+#pragma unroll
+		for (int j = -5; j <= 5; j += INC) {
+			const float rp = col[n * STRIDE];
+			++n;
+			const float yf = cyf + (float)j;
+			const f32x2 YF = pk2(yf, yf);
+			const f32x2 XS = add2(H.h[2], fma2(H.h[1], YF, AX));
+			const f32x2 YS = add2(H.h[5], fma2(H.h[4], YF, AY));
+			const f32x2 ZS = add2(H.h[8], fma2(H.h[7], YF, AZ));
+			float xs0, xs1, ys0, ys1, zs0, zs1;
+			unpk2(XS, xs0, xs1); unpk2(YS, ys0, ys1); unpk2(ZS, zs0, zs1);
+			float sp0 = 0.f, sp1 = 0.f;
+			if (w0) { const float rz = rcpf(zs0); sp0 = tex2DLayered<float>(tex, fmaf(xs0, rz, 0.5f), fmaf(ys0, rz, 0.5f), lay0); }
+			if (w1) { const float rz = rcpf(zs1); sp1 = tex2DLayered<float>(tex, fmaf(xs1, rz, 0.5f), fmaf(ys1, rz, 0.5f), lay1); }
+			const f32x2 SP = pk2(sp0, sp1), RP = pk2(rp, rp);
+			RS = fma2(RP, SP, RS); S = add2(S, SP); SS = fma2(SP, SP, SS);
+		}
+		TS = add2(TS, S); TSS = add2(TSS, SS); TRS = add2(TRS, RS);
+	}
+	NccSums t0 = {sum_r, sum_rr, 0.f, 0.f, 0.f}, t1 = t0;
+	unpk2(TS, t0.s, t1.s); unpk2(TSS, t0.ss, t1.ss); unpk2(TRS, t0.rs, t1.rs);
+	o0 = ncc_cost(t0, inv_w); o1 = ncc_cost(t1, inv_w);
+}
+
+// reference side of one window: taps in the evaluation order (x-offset outer, y-offset inner) and their sum / sum of
+// squares accumulated exactly as the evaluation would (APD.cu:456-487)
+template <int INC, int STRIDE>
+__device__ __forceinline__ void wq_cache_window(const Args &a, int cx, int cy, float *col, float *sums) {
+	const float *base = a.ref_pad + (size_t)(cy + kRefPad) * a.ref_pitch + (cx + kRefPad);
+	float R = 0.f, RR = 0.f;
+	int t = 0;
+#pragma unroll
+	for (int i = -5; i <= 5; i += INC) {
+		float r = 0.f, rr = 0.f;
+#pragma unroll
+		for (int j = -5; j <= 5; j += INC) {
+			const float rp = __ldg(base + (ptrdiff_t)j * a.ref_pitch + i);
+			col[t * STRIDE] = rp;
+			++t;
+			r += rp; rr = fmaf(rp, rp, rr);
+		}
+		R += r; RR += rr;
+	}
+	sums[0] = R; sums[STRIDE] = RR;
+}
+
+
+}  // namespace apd
