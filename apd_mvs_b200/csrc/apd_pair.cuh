@@ -95,6 +95,76 @@ __device__ __forceinline__ void wq_window2(cudaTextureObject_t tex, int lay0, in
 	o0 = ncc_cost(t0, inv_w); o1 = ncc_cost(t1, inv_w);
 }
 
+// The plain 6x6 window (INC = 2) for the two slots, WITHOUT per-slot predicates: unconditional fetches keep the code the
+// compiler emits per TEX down to the coordinate arithmetic (a predicated TEX makes ptxas rebuild the layer clamp, the LOD
+// register and the texture handle for every fetch: profiles/r02d_*); callers make sure both slots carry useful work and
+// discard the result of a slot that does not. PIPE: software-pipelined over the tap columns - the twelve fetches of the
+// next column are issued before the current one is accumulated, so a lane always has fetches in flight while it computes.
+// The loop stays rolled (two columns per trip): fully unrolled, the kernel no longer fits the instruction cache.
+template <int STRIDE>
+__device__ __forceinline__ void wq6_issue(cudaTextureObject_t tex, int lay0, int lay1, const Homog2 &H, float xf, const float (&yf)[6], f32x2 (&b)[6]) {
+	const f32x2 XF = pk2(xf, xf);
+	const f32x2 AX = mul2(H.h[0], XF), AY = mul2(H.h[3], XF), AZ = mul2(H.h[6], XF);
+#pragma unroll
+	for (int j = 0; j < 6; ++j) {
+		const f32x2 YF = pk2(yf[j], yf[j]);
+		const f32x2 XS = add2(H.h[2], fma2(H.h[1], YF, AX));
+		const f32x2 YS = add2(H.h[5], fma2(H.h[4], YF, AY));
+		const f32x2 ZS = add2(H.h[8], fma2(H.h[7], YF, AZ));
+		float xs0, xs1, ys0, ys1, zs0, zs1;
+		unpk2(XS, xs0, xs1); unpk2(YS, ys0, ys1); unpk2(ZS, zs0, zs1);
+		const float rz0 = rcpf(zs0), rz1 = rcpf(zs1);
+		const float sp0 = tex2DLayered<float>(tex, fmaf(xs0, rz0, 0.5f), fmaf(ys0, rz0, 0.5f), lay0);
+		const float sp1 = tex2DLayered<float>(tex, fmaf(xs1, rz1, 0.5f), fmaf(ys1, rz1, 0.5f), lay1);
+		b[j] = pk2(sp0, sp1);
+	}
+}
+template <int STRIDE>
+__device__ __forceinline__ void wq6_accum(const float *col, const f32x2 (&b)[6], f32x2 &TS, f32x2 &TSS, f32x2 &TRS) {
+	f32x2 RS = 0ull, S = 0ull, SS = 0ull;
+#pragma unroll
+	for (int j = 0; j < 6; ++j) {
+		const float rp = col[j * STRIDE];
+		const f32x2 SP = b[j], RP = pk2(rp, rp);
+		RS = fma2(RP, SP, RS); S = add2(S, SP); SS = fma2(SP, SP, SS);
+	}
+	TS = add2(TS, S); TSS = add2(TSS, SS); TRS = add2(TRS, RS);
+}
+template <int STRIDE, bool PIPE>
+__device__ __forceinline__ void wq_window6(cudaTextureObject_t tex, int lay0, int lay1, const Homog2 &H, int cx, int cy, float inv_w,
+                                           const float *col, float sum_r, float sum_rr, float &o0, float &o1) {
+	const float cxf = (float)cx, cyf = (float)cy;
+	float yf[6];
+#pragma unroll
+	for (int j = 0; j < 6; ++j) yf[j] = cyf + (float)(2 * j - 5);
+	f32x2 TS = 0ull, TSS = 0ull, TRS = 0ull;
+	if (PIPE) {
+		f32x2 bA[6], bB[6];
+		float xf = cxf - 5.0f;
+		wq6_issue<STRIDE>(tex, lay0, lay1, H, xf, yf, bA);
+#pragma unroll 1
+		for (int c = 0; c < 6; c += 2) {
+			wq6_issue<STRIDE>(tex, lay0, lay1, H, xf + 2.0f, yf, bB);
+			wq6_accum<STRIDE>(col + 6 * c * STRIDE, bA, TS, TSS, TRS);
+			xf += 4.0f;
+			if (c < 4) wq6_issue<STRIDE>(tex, lay0, lay1, H, xf, yf, bA);
+			wq6_accum<STRIDE>(col + 6 * (c + 1) * STRIDE, bB, TS, TSS, TRS);
+		}
+	} else {
+		float xf = cxf - 5.0f;
+#pragma unroll 1
+		for (int c = 0; c < 6; ++c) {
+			f32x2 bA[6];
+			wq6_issue<STRIDE>(tex, lay0, lay1, H, xf, yf, bA);
+			wq6_accum<STRIDE>(col + 6 * c * STRIDE, bA, TS, TSS, TRS);
+			xf += 2.0f;
+		}
+	}
+	NccSums t0 = {sum_r, sum_rr, 0.f, 0.f, 0.f}, t1 = t0;
+	unpk2(TS, t0.s, t1.s); unpk2(TSS, t0.ss, t1.ss); unpk2(TRS, t0.rs, t1.rs);
+	o0 = ncc_cost(t0, inv_w); o1 = ncc_cost(t1, inv_w);
+}
+
 // reference side of one window: taps in the evaluation order (x-offset outer, y-offset inner) and their sum / sum of
 // squares accumulated exactly as the evaluation would (APD.cu:456-487)
 template <int INC, int STRIDE>

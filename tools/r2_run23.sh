@@ -1,0 +1,10 @@
+#!/bin/bash
+set -u
+cd /root/repo; mkdir -p gpurun_out; rm -f gpurun_out/time_ours.jsonl
+timeout 900 python -m pytest tests/test_parity_gpu.py -x -q 2>&1 | tail -5
+for c in cfg3 cfg2 cfg3s mid; do
+timeout 300 python tests/tools/time_ours.py $c 2 sweepq2 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['case'], d['crc']['planes'], d['crc']['states'], d['iter_ms'], d['total_ms'], 'K14', d['stage_ms']['K14 classify'])"
+done
+for c in cfg3 cfg2; do
+APD_SQ_BLOCKS=3 timeout 300 python tests/tools/time_ours.py $c 2 sweepq2_3b 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('3 blocks', d['case'], d['crc']['planes'], d['crc']['states'], d['iter_ms'], d['total_ms'], 'K14', d['stage_ms']['K14 classify'])"
+done
