@@ -402,10 +402,11 @@ cudaError_t launch_sweep_q(cudaStream_t st, const Args &a, int mode, int num_sms
 	int *work = a.wctrl + 3 + mode;                        // wctrl[3..5]: zeroed at the start of every run
 	static const int minb = [] { const char *e = getenv("APD_SQ_BLOCKS"); return e ? atoi(e) : 4; }();
 	static const int pipe = [] { const char *e = getenv("APD_SQ_PIPE"); return e ? atoi(e) : 0; }();
-#define SQ(A, B) (minb == 3 ? (pipe ? launch_sweep_q_t<A, B, 3, true>(st, a, work, num_sms, smem) : launch_sweep_q_t<A, B, 3, false>(st, a, work, num_sms, smem)) \
-                            : (pipe ? launch_sweep_q_t<A, B, 4, true>(st, a, work, num_sms, smem) : launch_sweep_q_t<A, B, 4, false>(st, a, work, num_sms, smem)))
+#define SQB(A, B, N) (pipe ? launch_sweep_q_t<A, B, N, true>(st, a, work, num_sms, smem) : launch_sweep_q_t<A, B, N, false>(st, a, work, num_sms, smem))
+#define SQ(A, B) (minb == 3 ? SQB(A, B, 3) : minb == 5 ? SQB(A, B, 5) : SQB(A, B, 4))
 	return mode == 0 ? SQ(true, false) : mode == 1 ? SQ(false, true) : SQ(true, true);
 #undef SQ
+#undef SQB
 }
 
 }  // namespace apd

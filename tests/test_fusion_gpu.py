@@ -1,8 +1,8 @@
 """GPU parity of the depth-map fusion (include/apd_fusion.h) against the reference's UNMODIFIED RunFusion
 (APD.cpp:826-977 compiled behind oracle/shim_host, run on the host CPU) on the same depth / normal / state maps,
 which come from a real run of the pass schedule. Bar: the same points in the same order; coordinates and colours
-bit-identical. The only operations that may legitimately differ between glibc and CUDA are acosf / expf in their last
-bit, which can flip a threshold for a handful of pixels: the test allows 1e-4 of the points to differ and reports it."""
+bit-identical, pinned at ZERO differing points. (The only operations that could legitimately differ between glibc and CUDA are
+acosf / expf in their last bit; on these inputs no value sits on a threshold.)"""
 import numpy as np
 import pytest
 
