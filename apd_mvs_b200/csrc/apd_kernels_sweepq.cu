@@ -43,6 +43,8 @@ constexpr int kSqWarpWords = (kSqRef + kSqProf + kSqNear) * kSqPix + 2 * kSqCtxR
 // context flags
 constexpr int kFNeed = 1, kFInRange = 2, kFStore15 = 4, kFWant14 = 8;
 constexpr int kSqTileW = 8, kSqTileH = 4;  // one chunk
+constexpr int kSqBlocks = 4;               // resident blocks per SM the register allocation is sized for (128 registers, no spills;
+                                           // measured: 5 blocks at 96 registers 291 ms, 3 at 168 341 ms, 4: 274 ms at 6221x4146)
 
 // ComputeGeomConsistencyCost's view-dependent half (geom_cost_at, apd_device.cuh) for the two slots: world point P0
 // against source view va, P1 against vb. Negations sit on an operand ((-x)*y == -(x*y) exactly); subtractions are additions of
@@ -89,9 +91,8 @@ __device__ __forceinline__ void geom_cost_at2(const Args &a, const RefConst &rc,
 	g1 = (sd1 == 0.0f) ? 3.0f : fminf(sqrtaf(e1), 3.0f);
 }
 
-// MINB = resident blocks per SM the register allocation is sized for
-template <bool DO14, bool DO15, int MINB, bool PIPE>
-__global__ void __launch_bounds__(kSqNT, MINB) k_sweep_q(const Args a, int *work, const int tiles_x, const int nchunks) {
+template <bool DO14, bool DO15>
+__global__ void __launch_bounds__(kSqNT, kSqBlocks) k_sweep_q(const Args a, int *work, const int tiles_x, const int nchunks) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	RefConst *sr = reinterpret_cast<RefConst *>(smem_raw);
 	ViewConst *sv = reinterpret_cast<ViewConst *>(sr + 1);
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kSqNT, MINB) k_sweep_q(const Args a, int *work
 			in1 = !(x1 >= vc1.wf || x1 < 0.0f || y1 >= vc1.hf || y1 < 0.0f);
 		}
 		float c0, c1;
-		wq_window6<kSqPix, PIPE>(a.img_tex, v0 + 1, v1 + 1, H, px, py, inv36, refc, refc[36 * kSqPix], refc[37 * kSqPix], c0, c1);
+		wq_window6<kSqPix>(a.img_tex, v0 + 1, v1 + 1, H, px, py, inv36, refc, refc[36 * kSqPix], refc[37 * kSqPix], c0, c1);
 		if (!in0) c0 = kCostMax;
 		if (!in1) c1 = kCostMax;
 		float g0 = 0.f, g1 = 0.f;
@@ -384,29 +385,24 @@ __global__ void __launch_bounds__(kSqNT, MINB) k_sweep_q(const Args a, int *work
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool DO14, bool DO15, int MINB, bool PIPE>
+template <bool DO14, bool DO15>
 static cudaError_t launch_sweep_q_t(cudaStream_t st, const Args &a, int *work, int num_sms, size_t smem) {
-	cudaError_t e = cudaFuncSetAttribute(k_sweep_q<DO14, DO15, MINB, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(k_sweep_q<DO14, DO15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_q<DO14, DO15, MINB, PIPE>, kSqNT, smem);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_q<DO14, DO15>, kSqNT, smem);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) per_sm = 1;
 	const int tiles_x = (a.W + kSqTileW - 1) / kSqTileW, tiles_y = (a.H + kSqTileH - 1) / kSqTileH;
-	k_sweep_q<DO14, DO15, MINB, PIPE><<<num_sms * per_sm, kSqNT, smem, st>>>(a, work, tiles_x, tiles_x * tiles_y);
+	k_sweep_q<DO14, DO15><<<num_sms * per_sm, kSqNT, smem, st>>>(a, work, tiles_x, tiles_x * tiles_y);
 	return cudaGetLastError();
 }
 // mode 0: K14 only, 1: K15 only, 2: K14+K15 fused (as launch_sweep)
 cudaError_t launch_sweep_q(cudaStream_t st, const Args &a, int mode, int num_sms) {
 	const size_t smem = sizeof(RefConst) + (size_t)a.S * sizeof(ViewConst) + (size_t)(kSqNT / 32) * kSqWarpWords * 4;
 	int *work = a.wctrl + 3 + mode;                        // wctrl[3..5]: zeroed at the start of every run
-	static const int minb = [] { const char *e = getenv("APD_SQ_BLOCKS"); return e ? atoi(e) : 4; }();
-	static const int pipe = [] { const char *e = getenv("APD_SQ_PIPE"); return e ? atoi(e) : 0; }();
-#define SQB(A, B, N) (pipe ? launch_sweep_q_t<A, B, N, true>(st, a, work, num_sms, smem) : launch_sweep_q_t<A, B, N, false>(st, a, work, num_sms, smem))
-#define SQ(A, B) (minb == 3 ? SQB(A, B, 3) : minb == 5 ? SQB(A, B, 5) : SQB(A, B, 4))
-	return mode == 0 ? SQ(true, false) : mode == 1 ? SQ(false, true) : SQ(true, true);
-#undef SQ
-#undef SQB
+	return mode == 0 ? launch_sweep_q_t<true, false>(st, a, work, num_sms, smem)
+	     : mode == 1 ? launch_sweep_q_t<false, true>(st, a, work, num_sms, smem) : launch_sweep_q_t<true, true>(st, a, work, num_sms, smem);
 }
 
 }  // namespace apd

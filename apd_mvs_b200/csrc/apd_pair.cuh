@@ -98,9 +98,9 @@ __device__ __forceinline__ void wq_window2(cudaTextureObject_t tex, int lay0, in
 // The plain 6x6 window (INC = 2) for the two slots, WITHOUT per-slot predicates: unconditional fetches keep the code the
 // compiler emits per TEX down to the coordinate arithmetic (a predicated TEX makes ptxas rebuild the layer clamp, the LOD
 // register and the texture handle for every fetch: profiles/r02d_*); callers make sure both slots carry useful work and
-// discard the result of a slot that does not. PIPE: software-pipelined over the tap columns - the twelve fetches of the
-// next column are issued before the current one is accumulated, so a lane always has fetches in flight while it computes.
-// The loop stays rolled (two columns per trip): fully unrolled, the kernel no longer fits the instruction cache.
+// discard the result of a slot that does not. The loop over the six tap columns stays ROLLED (12 fetches per trip): fully
+// unrolled and software-pipelined the kernel no longer fits the instruction cache (383 vs 295 ms at 6221x4146), and a rolled
+// two-column pipeline was no faster either (309 ms: the other warps already cover the fetch latency).
 template <int STRIDE>
 __device__ __forceinline__ void wq6_issue(cudaTextureObject_t tex, int lay0, int lay1, const Homog2 &H, float xf, const float (&yf)[6], f32x2 (&b)[6]) {
 	const f32x2 XF = pk2(xf, xf);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void wq6_accum(const float *col, const f32x2 (&b)[6],
 	}
 	TS = add2(TS, S); TSS = add2(TSS, SS); TRS = add2(TRS, RS);
 }
-template <int STRIDE, bool PIPE>
+template <int STRIDE>
 __device__ __forceinline__ void wq_window6(cudaTextureObject_t tex, int lay0, int lay1, const Homog2 &H, int cx, int cy, float inv_w,
                                            const float *col, float sum_r, float sum_rr, float &o0, float &o1) {
 	const float cxf = (float)cx, cyf = (float)cy;
@@ -138,27 +138,13 @@ __device__ __forceinline__ void wq_window6(cudaTextureObject_t tex, int lay0, in
 #pragma unroll
 	for (int j = 0; j < 6; ++j) yf[j] = cyf + (float)(2 * j - 5);
 	f32x2 TS = 0ull, TSS = 0ull, TRS = 0ull;
-	if (PIPE) {
-		f32x2 bA[6], bB[6];
-		float xf = cxf - 5.0f;
-		wq6_issue<STRIDE>(tex, lay0, lay1, H, xf, yf, bA);
+	float xf = cxf - 5.0f;
 #pragma unroll 1
-		for (int c = 0; c < 6; c += 2) {
-			wq6_issue<STRIDE>(tex, lay0, lay1, H, xf + 2.0f, yf, bB);
-			wq6_accum<STRIDE>(col + 6 * c * STRIDE, bA, TS, TSS, TRS);
-			xf += 4.0f;
-			if (c < 4) wq6_issue<STRIDE>(tex, lay0, lay1, H, xf, yf, bA);
-			wq6_accum<STRIDE>(col + 6 * (c + 1) * STRIDE, bB, TS, TSS, TRS);
-		}
-	} else {
-		float xf = cxf - 5.0f;
-#pragma unroll 1
-		for (int c = 0; c < 6; ++c) {
-			f32x2 bA[6];
-			wq6_issue<STRIDE>(tex, lay0, lay1, H, xf, yf, bA);
-			wq6_accum<STRIDE>(col + 6 * c * STRIDE, bA, TS, TSS, TRS);
-			xf += 2.0f;
-		}
+	for (int c = 0; c < 6; ++c) {
+		f32x2 b[6];
+		wq6_issue<STRIDE>(tex, lay0, lay1, H, xf, yf, b);
+		wq6_accum<STRIDE>(col + 6 * c * STRIDE, b, TS, TSS, TRS);
+		xf += 2.0f;
 	}
 	NccSums t0 = {sum_r, sum_rr, 0.f, 0.f, 0.f}, t1 = t0;
 	unpk2(TS, t0.s, t1.s); unpk2(TSS, t0.ss, t1.ss); unpk2(TRS, t0.rs, t1.rs);

@@ -244,3 +244,18 @@ def test_random_configurations_bit_exact():
         case = T.build_case(W, H, S, device="cuda", **kw)
         d = T.final_diff(case, curand_seed)
         assert all(v == 0.0 for v in d.values()), (i, W, H, S, kw, d)
+
+
+def test_first_design_kernels_stay_bit_exact():
+    """The first-design kernels kept for A/B timing (`APD_WEAK_IMPL=old`: thread-per-pixel k_weak, `APD_SWEEP_IMPL=old`:
+    thread-per-pixel k_sweep) must stay bit-identical to the golden fixtures too. The choice is read once per handle from
+    the environment, so the golden tests are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, APD_WEAK_IMPL="old", APD_SWEEP_IMPL="old")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_parity_gpu.py"), "-q", "-x", "-k", "test_golden_bit_exact"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f"{len(GOLDEN)} passed" in r.stdout, r.stdout[-500:]
