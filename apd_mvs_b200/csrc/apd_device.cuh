@@ -489,6 +489,7 @@ __device__ __forceinline__ void vw_store(uint4 *g, size_t i, const VW &w) { g[i]
 // bitmask of the views with a non-zero sampling weight
 __device__ __forceinline__ uint32_t vw_mask(const VW &w, int S) {
 	uint32_t m = 0u;
+#pragma unroll 1
 	for (int v = 0; v < S; ++v) if (vw_get(w, v) > 0) m |= 1u << v;
 	return m;
 }
@@ -505,6 +506,7 @@ __device__ __forceinline__ bool sweep_setup(const Args &a, const RefConst &rc, c
 	c.pl.w = in.w; c.depth = in.w;
 	if (c.depth == 0.0f) return false;
 	float base = 0.0f; c.weight_normal = 0.0f; c.valid = 0;
+#pragma unroll 1
 	for (int v = 0; v < a.S; ++v) if ((bits >> v) & 1u) { base += sv[v].baseline; c.weight_normal += (float)vw_get(vw, v); c.valid++; }
 	if (c.valid == 0) return true;
 	base = rcpf((float)c.valid) * base;

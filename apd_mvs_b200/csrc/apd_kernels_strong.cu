@@ -131,6 +131,7 @@ __device__ __forceinline__ void load_views(const Args &a, ViewConst *sv, RefCons
 	const int n = a.S * (int)(sizeof(ViewConst) / 4);
 	const uint32_t *g = reinterpret_cast<const uint32_t *>(a.views);
 	uint32_t *s = reinterpret_cast<uint32_t *>(sv);
+#pragma unroll 1
 	for (int i = tid; i < n; i += nt) s[i] = g[i];
 	const uint32_t *gr = reinterpret_cast<const uint32_t *>(a.ref);
 	uint32_t *srr = reinterpret_cast<uint32_t *>(sr);
@@ -428,25 +429,30 @@ __global__ void __launch_bounds__(NT, 4) k_strong(const Args a, const int iter, 
 		{
 			const float inv = rcpf(prob_sum);
 			float cum = 0.0f;
+#pragma unroll 1
 			for (int v = 0; v < S; ++v) { cum = fmaf(inv, PROB(v), cum); PROB(v) = cum; }   // TransformPDFToCDF
+#pragma unroll 1
 			for (int s = 0; s < 15; ++s) {
 				const float r = rng_uniform(rng) - 1.1920928955078125e-07f;
+#pragma unroll 1
 				for (int v = 0; v < S; ++v) if (PROB(v) > r) { vw_add(vw, v); break; }
 			}
 		}
 		float weight_norm = 0.0f;
+#pragma unroll 1
 		for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) { temp_sel |= 1u << v; weight_norm += (float)w; } }
 		inv_wn = rcpf(weight_norm);
-		float fc[8];
-#pragma unroll
+		// final costs of the eight candidates and their minimum. Rolled on purpose: this runs once per pixel, and unrolled (8 x S with the
+		// nibble extraction of the weights) it was 2 900 of the kernel's 7 600 SASS instructions - instruction-cache footprint the hot loops pay for
+		best_cost = 0.0f; best_k = 0;             // FindMinCostIndex: `<=`, last minimum wins (APD.cu:29-40)
+#pragma unroll 1
 		for (int k = 0; k < 8; ++k) {
 			float acc = 0.0f;
+#pragma unroll 1
 			for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) acc = fmaf((float)w, CM(k, v), acc); }
-			fc[k] = acc * inv_wn;
+			const float fck = acc * inv_wn;
+			if (k == 0 || fck <= best_cost) { best_cost = fck; best_k = k; }
 		}
-		best_cost = fc[0]; best_k = 0;            // FindMinCostIndex: `<=`, last minimum wins (APD.cu:29-40)
-#pragma unroll
-		for (int k = 1; k < 8; ++k) if (fc[k] <= best_cost) { best_cost = fc[k]; best_k = k; }
 	}
 
 	// ---- current hypothesis under the sampled views (views with weight 0 contribute exactly 0)

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kSqNT, kSqBlocks) k_sweep_q(const Args a, int 
 	{
 		const int nv = S * (int)(sizeof(ViewConst) / 4);
 		const uint32_t *g = reinterpret_cast<const uint32_t *>(a.views); uint32_t *s = reinterpret_cast<uint32_t *>(sv);
+#pragma unroll 1
 		for (int i = tid; i < nv; i += kSqNT) s[i] = g[i];
 		const uint32_t *gr = reinterpret_cast<const uint32_t *>(a.ref); uint32_t *srr = reinterpret_cast<uint32_t *>(sr);
 		for (int i = tid; i < (int)(sizeof(RefConst) / 4); i += kSqNT) srr[i] = gr[i];

@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kWqNT, MINB) k_weak_q(const Args a, const int 
 	{
 		const int nv = S * (int)(sizeof(ViewConst) / 4);
 		const uint32_t *g = reinterpret_cast<const uint32_t *>(a.views); uint32_t *s = reinterpret_cast<uint32_t *>(sv);
+#pragma unroll 1
 		for (int i = tid; i < nv; i += kWqNT) s[i] = g[i];
 		const uint32_t *gr = reinterpret_cast<const uint32_t *>(a.ref); uint32_t *srr = reinterpret_cast<uint32_t *>(sr);
 		for (int i = tid; i < (int)(sizeof(RefConst) / 4); i += kWqNT) srr[i] = gr[i];
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(kWqNT, MINB) k_weak_q(const Args a, const int 
 					const float thr = 0.8 * __expf((float)(unsigned)(iter * iter) * -0.011111111380159854889f);
 					const float thr_fallback = __expf((thr * thr) * -3.125f);
 					float prob_sum = 0.0f;
+#pragma unroll 1
 					for (int v = 0; v < S; ++v) {
 						float prior = 0.0f;
 						for (int k = 1; k < APD_NEIGHBOUR_NUM; ++k) {
@@ -311,19 +313,24 @@ __global__ void __launch_bounds__(kWqNT, MINB) k_weak_q(const Args a, const int 
 					{
 						const float inv = rcpf(prob_sum); float cum = 0.0f;
 						// the four lanes hold identical copies of the CDF; lane 0 keeps it in shared memory
+#pragma unroll 1
 						for (int v = 0; v < S; ++v) { cum = fmaf(inv, PROB(v), cum); __syncwarp(qmask); if (ql == 0) PROB(v) = cum; __syncwarp(qmask); }
+#pragma unroll 1
 						for (int s = 0; s < 15; ++s) {
 							const float r = rng_uniform(rng) - 1.1920928955078125e-07f;
+#pragma unroll 1
 							for (int v = 0; v < S; ++v) if (PROB(v) > r) { vw_add(vw, v); break; }
 						}
 					}
 					float weight_norm = 0.0f;
+#pragma unroll 1
 					for (int v = 0; v < S; ++v) { const int w = vw_get(vw, v); if (w > 0) { temp_sel |= 1u << v; weight_norm += (float)w; } }
 					inv_wn = rcpf(weight_norm);
 					// final costs of the eight candidates (APD.cu:1436-1452): lane l computes candidates l and l+4
 					float fcr0 = 0.f, fcr1 = 0.f;
 					{
 						float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
 						for (int v = 0; v < S; ++v) {
 							const int w = vw_get(vw, v);
 							if (w == 0) continue;
