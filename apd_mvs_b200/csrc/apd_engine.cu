@@ -98,6 +98,8 @@ extern "C" int apd_create(apd_handle *out, int device, int width, int height, in
 	auto bail = [&](int code) { apd_destroy(h); return code; };
 	if (cudaSetDevice(device) != cudaSuccess) return bail(APD_E_CUDA);
 	if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(APD_E_CUDA);
+	if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(APD_E_CUDA);
+	if (cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_late, cudaEventDisableTiming) != cudaSuccess) return bail(APD_E_CUDA);
 	const size_t n = h->npx;
 	h->ref_pitch = ((width + 2 * kRefPad + 3) / 4) * 4;
 	h->ref_rows = height + 2 * kRefPad;
@@ -152,6 +154,9 @@ extern "C" void apd_destroy(apd_handle h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	if (h->stream) cudaStreamSynchronize(h->stream);
+	if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+	if (h->ev_early) cudaEventDestroy(h->ev_early);
+	if (h->ev_late) cudaEventDestroy(h->ev_late);
 	for (auto e : h->events) cudaEventDestroy(e);
 	if (h->img_tex) cudaDestroyTextureObject(h->img_tex);
 	if (h->depth_tex) cudaDestroyTextureObject(h->depth_tex);
@@ -189,18 +194,41 @@ extern "C" int apd_reset_inputs(apd_handle h) {
 }
 extern "C" int apd_get_capacity(apd_handle h) { return h ? h->capacity : 0; }
 
+extern "C" int apd_set_upload_mode(apd_handle h, int asynchronous) {
+	if (!h) return APD_E_ARG;
+	CKH(cudaSetDevice(h->device));
+	if (h->async_upload && !asynchronous) { CKH(cudaStreamSynchronize(h->copy_stream)); h->pending_early = h->pending_late = false; }
+	h->async_upload = asynchronous != 0;
+	return APD_OK;
+}
+// Stream a host upload goes to, and what ends it: a wait (default) or an event the run waits for (asynchronous mode).
+static inline cudaStream_t upload_stream(apd_handle h, bool host) { return (h->async_upload && host) ? h->copy_stream : h->stream; }
+static int finish_upload(apd_handle h, bool host, bool late) {
+	if (h->async_upload && host) {
+		CKH(cudaEventRecord(late ? h->ev_late : h->ev_early, h->copy_stream));
+		(late ? h->pending_late : h->pending_early) = true;
+		return APD_OK;
+	}
+	CKH(cudaStreamSynchronize(h->stream));
+	return APD_OK;
+}
+
 extern "C" int apd_set_cameras(apd_handle h, const apd_camera *cams) {
 	if (!h || !cams) return APD_E_ARG;
 	CKH(cudaSetDevice(h->device));
 	for (int i = 0; i < h->N; ++i)
 		if (cams[i].width != h->W || cams[i].height != h->H) return fail(h, APD_E_ARG, "camera width/height must equal the image size (APD.cpp:439-449)");
-	CKH(cudaMemcpyAsync(h->d_cams, cams, sizeof(apd_camera) * h->N, cudaMemcpyHostToDevice, h->stream));
-	CKH(cudaStreamSynchronize(h->stream));
+	if (h->async_upload) {   // the caller's array may be a temporary (112 B per camera): keep our own copy until the run
+		h->cams_host.assign(cams, cams + h->N);
+		CKH(cudaMemcpyAsync(h->d_cams, h->cams_host.data(), sizeof(apd_camera) * h->N, cudaMemcpyHostToDevice, h->copy_stream));
+	} else CKH(cudaMemcpyAsync(h->d_cams, cams, sizeof(apd_camera) * h->N, cudaMemcpyHostToDevice, h->stream));
+	{ int rc = finish_upload(h, true, false); if (rc) return rc; }
 	h->have_cams = true;
 	return APD_OK;
 }
 
 static int copy_stack(apd_handle h, cudaArray_t arr, const float *const *host_imgs, const float *dev_stack, size_t pitch, size_t stride) {
+	cudaStream_t st = upload_stream(h, host_imgs != nullptr);
 	for (int i = 0; i < h->N; ++i) {
 		cudaMemcpy3DParms p; memset(&p, 0, sizeof(p));
 		const float *src = host_imgs ? host_imgs[i] : (const float *)((const char *)dev_stack + (size_t)i * stride);
@@ -208,16 +236,17 @@ static int copy_stack(apd_handle h, cudaArray_t arr, const float *const *host_im
 		p.dstArray = arr; p.dstPos = make_cudaPos(0, 0, i);
 		p.extent = make_cudaExtent(h->W, h->H, 1);
 		p.kind = cudaMemcpyDefault;      // host or device pointers (unified addressing)
-		CKH(cudaMemcpy3DAsync(&p, h->stream));
+		CKH(cudaMemcpy3DAsync(&p, st));
 	}
 	return APD_OK;
 }
 
 static int finish_images(apd_handle h, const float *img0, size_t pitch, bool host) {
-	CKH(cudaMemcpy2DAsync(h->ref_lin, (size_t)h->W * 4, img0, pitch, (size_t)h->W * 4, h->H, cudaMemcpyDefault, h->stream));
-	launch_pad_ref(h->stream, h->ref_lin, h->W, h->H, h->W, h->ref_pad, h->ref_pitch, h->ref_rows);
+	cudaStream_t st = upload_stream(h, host);
+	CKH(cudaMemcpy2DAsync(h->ref_lin, (size_t)h->W * 4, img0, pitch, (size_t)h->W * 4, h->H, cudaMemcpyDefault, st));
+	launch_pad_ref(st, h->ref_lin, h->W, h->H, h->W, h->ref_pad, h->ref_pitch, h->ref_rows);
 	CKH(cudaGetLastError());
-	CKH(cudaStreamSynchronize(h->stream));
+	{ int rc = finish_upload(h, host, true); if (rc) return rc; }
 	h->have_images = true;
 	return APD_OK;
 }
@@ -244,7 +273,7 @@ extern "C" int apd_set_depths(apd_handle h, const float *const *depths, size_t p
 	CKH(cudaSetDevice(h->device));
 	int rc = ensure_depth_array(h); if (rc) return rc;
 	rc = copy_stack(h, h->depth_arr, depths, nullptr, pitch_bytes, 0); if (rc) return rc;
-	CKH(cudaStreamSynchronize(h->stream));
+	rc = finish_upload(h, true, true); if (rc) return rc;
 	h->have_depths = true;
 	return APD_OK;
 }
@@ -262,18 +291,22 @@ extern "C" int apd_set_priors(apd_handle h, const float *planes, const uint32_t 
 	if (!h) return APD_E_ARG;
 	CKH(cudaSetDevice(h->device));
 	const size_t n = h->npx;
+	// host or device pointers: only host memory takes the copy stream in asynchronous mode
+	auto is_host = [](const void *p) { cudaPointerAttributes at; return cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeUnregistered; };
+	const bool host = (planes ? is_host(planes) : true) && (states ? is_host(states) : true);
+	cudaGetLastError();
+	cudaStream_t st = upload_stream(h, host);
 	if (planes) {
 		if (!views) return fail(h, APD_E_ARG, "planes need views (APD.cpp:552-581)");
-		CKH(cudaMemcpyAsync(h->prior_planes, planes, n * 16, cudaMemcpyDefault, h->stream));
-		CKH(cudaMemcpyAsync(h->prior_views, views, n * 4, cudaMemcpyDefault, h->stream));
+		CKH(cudaMemcpyAsync(h->prior_planes, planes, n * 16, cudaMemcpyDefault, st));
+		CKH(cudaMemcpyAsync(h->prior_views, views, n * 4, cudaMemcpyDefault, st));
 		h->have_planes = true;
 	}
 	if (states) {
-		CKH(cudaMemcpyAsync(h->prior_states, states, n, cudaMemcpyDefault, h->stream));
+		CKH(cudaMemcpyAsync(h->prior_states, states, n, cudaMemcpyDefault, st));
 		h->have_states = true;
 	}
-	CKH(cudaStreamSynchronize(h->stream));
-	return APD_OK;
+	return finish_upload(h, host, false);
 }
 
 extern "C" int apd_num_stages(apd_handle h) { return h ? 10 + 5 * h->params.max_iterations : 0; }
@@ -315,6 +348,8 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	h->launches = 0;
 	const bool apd_on = p.use_APD != 0;
 
+	// ---- asynchronous uploads: cameras and priors are read by the very first operations
+	if (h->pending_early) { CKH(cudaStreamWaitEvent(st, h->ev_early, 0)); }
 	// ---- restore the run's inputs (what CudaSpaceInitialization uploads, APD.cpp:643-661)
 	if (apd_on) CKH(cudaMemcpyAsync(h->states, h->prior_states, n, cudaMemcpyDeviceToDevice, st));
 	else CKH(cudaMemsetAsync(h->states, APD_STRONG, n, st));                       // APD.cpp:540-548
@@ -345,6 +380,7 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 		if (h->weak_impl == 1) { CKH(launch_weak_lists(st, a, true)); h->launches++; }
 	}
 	STAGE_END();
+	if (h->pending_late) { CKH(cudaStreamWaitEvent(st, h->ev_late, 0)); }     // images, padded reference, depth maps: first read by K5
 	CKH(launch_init_planes(st, a)); h->launches++; STAGE_END();                                            // 4  K5
 	for (int it = 0; it < p.max_iterations; ++it) {
 		CKH(launch_strong(st, a, it, 0, &h->tmap_strong)); h->launches++; STAGE_END();                                      // K6
@@ -364,6 +400,9 @@ extern "C" int apd_run_until(apd_handle h, int stage_end) {
 #undef STAGE_END
 done:
 	CKH(cudaStreamSynchronize(st));
+	if (h->pending_early || h->pending_late) {   // the host buffers are free again when the run returns, whatever stage it stopped at
+		CKH(cudaStreamSynchronize(h->copy_stream)); h->pending_early = h->pending_late = false;
+	}
 	h->stages_run = stage + 1;
 	h->stage_ms.assign(nstages, 0.0f);
 	for (int i = 0; i < h->stages_run; ++i) cudaEventElapsedTime(&h->stage_ms[i], h->events[i], h->events[i + 1]);

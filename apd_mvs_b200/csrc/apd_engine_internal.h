@@ -14,6 +14,10 @@ struct apd_engine {
 	apd_params params;
 	uint64_t seed = 0;
 	cudaStream_t stream = nullptr;
+	// asynchronous upload mode (apd_set_upload_mode): host copies go to copy_stream, the run waits for these events
+	cudaStream_t copy_stream = nullptr; cudaEvent_t ev_early = nullptr, ev_late = nullptr;   // early: cameras + priors, late: images + depth maps
+	bool async_upload = false, pending_early = false, pending_late = false;
+	std::vector<apd_camera> cams_host;
 	cudaArray_t img_arr = nullptr, depth_arr = nullptr;
 	cudaTextureObject_t img_tex = 0, depth_tex = 0;
 	float *ref_lin = nullptr, *ref_pad = nullptr;

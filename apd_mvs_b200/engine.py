@@ -61,6 +61,7 @@ def _load(path: str) -> C.CDLL:
     lib.apd_reset_inputs.argtypes = [vp]
     lib.apd_get_capacity.argtypes = [vp]
     lib.apd_set_num_images.argtypes = [vp, ci]
+    lib.apd_set_upload_mode.argtypes = [vp, ci]
     lib.apd_set_cameras.argtypes = [vp, vp]
     lib.apd_set_images.argtypes = [vp, C.POINTER(vp), C.c_size_t]
     lib.apd_set_images_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t]

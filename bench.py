@@ -272,12 +272,16 @@ def run_ours(wl_name, args, rank, world, local, torch, np, dist, full=True):
     vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
 
     def e2e_step(h):
-        rc = L.apd_set_cameras(h, C.c_void_p(cam_arr.ctypes.data))
+        # asynchronous upload mode of the C-ABI (apd_set_upload_mode): the calls enqueue their copies from the pinned host
+        # buffers and apd_run makes every launch wait for the inputs it reads - cameras + priors first (the first launches
+        # read them), then the image and depth stacks, whose transfer overlaps K1..K4
+        rc = L.apd_set_upload_mode(h, 1)
+        rc |= L.apd_set_cameras(h, C.c_void_p(cam_arr.ctypes.data))
+        if pl_host is not None or st_host is not None:
+            rc |= L.apd_set_priors(h, vp(pl_host), vp(vw_host), vp(st_host))
         rc |= L.apd_set_images(h, img_ptrs, W * 4)
         if dep_host is not None:
             rc |= L.apd_set_depths(h, dep_ptrs, W * 4)
-        if pl_host is not None or st_host is not None:
-            rc |= L.apd_set_priors(h, vp(pl_host), vp(vw_host), vp(st_host))
         rc |= L.apd_run(h)
         rc |= L.apd_get_planes(h, vp(out_planes)); rc |= L.apd_get_states(h, vp(out_states)); rc |= L.apd_get_views(h, vp(out_views))
         if rc:

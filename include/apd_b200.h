@@ -107,6 +107,16 @@ int apd_reset_inputs(apd_handle h);
 /* Image count the handle was created for (upper bound of apd_set_num_images). */
 int apd_get_capacity(apd_handle h);
 
+/* Upload mode of apd_set_cameras / apd_set_images / apd_set_depths / apd_set_priors with HOST pointers.
+ *   0 (default): every call returns when its copy has completed; the host buffer may be reused at once.
+ *   1 (asynchronous): the calls only enqueue their copies on the handle's copy stream and return; apd_run makes each
+ *     launch wait for exactly the inputs it reads (cameras + priors before the first launch, images + depth maps before
+ *     RandomInitialization), so the uploads of the image and depth stacks overlap InitRandomStates / FindNearestStrongPoint /
+ *     GenNeighbours. The caller keeps the host buffers valid and unchanged until apd_run / apd_run_until returns (pinned
+ *     host memory for a real overlap). The *_device variants are not affected. The reference uploads synchronously
+ *     inside CudaSpaceInitialization (APD.cpp:585-671). */
+int apd_set_upload_mode(apd_handle h, int asynchronous);
+
 /* cams[num_images]; index 0 is the reference view (APD.cpp:633-634). */
 int apd_set_cameras(apd_handle h, const apd_camera *cams);
 /* images[num_images]: pointers to float32 grey images (0..255), all width x height, rows `pitch_bytes` apart

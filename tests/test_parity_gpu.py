@@ -259,3 +259,45 @@ def test_first_design_kernels_stay_bit_exact():
                        env=env, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert f"{len(GOLDEN)} passed" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_asynchronous_upload_mode_is_bit_exact(pinned):
+    """apd_set_upload_mode(h, 1): the set calls only enqueue their copies, apd_run orders every launch behind the inputs it
+    reads. Same outputs as the default (synchronous) uploads, from pinned and from pageable host memory, on a handle that
+    is re-used for a second problem with other inputs."""
+    import ctypes as C
+    import torch
+    L = E.lib()
+    cases = [T.build_case(203, 131, 3, state=E.REFINE_ITER, geom=True, use_apd=True, iters=2, seed=s) for s in (11, 12)]
+    want = []
+    for case in cases:
+        apd = T.make_product(case); apd.RunPatchMatch(); want.append(T.product_state(apd)); apd.close()
+    h = C.c_void_p(None)
+    p = T.clone_params(cases[0]["params"])
+    W, H, S = 203, 131, 3
+    p.num_images = S + 1                              # what InuputInitialization derives (APD.cpp:454-455)
+    p.depth_min = float(np.float32(cases[0]["cameras"][0]["depth_min"]) * np.float32(0.6))
+    p.depth_max = float(np.float32(cases[0]["cameras"][0]["depth_max"]) * np.float32(1.2))
+    assert L.apd_create(C.byref(h), 0, W, H, S + 1, C.byref(p), T.CURAND_SEED) == 0
+    assert L.apd_set_upload_mode(h, 1) == 0
+    hold = lambda a: (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() if pinned else torch.from_numpy(np.ascontiguousarray(a).copy()))
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    for case, ref in zip(cases, want):
+        cams = np.ascontiguousarray(case["cameras"])
+        imgs, deps = hold(case["images"]), hold(case["depths"])
+        pl, vw, st = hold(case["planes"]), hold(case["views"].view(np.int32)), hold(case["states"])
+        ptrs = lambda t: (C.c_void_p * (S + 1))(*[t.data_ptr() + i * W * H * 4 for i in range(S + 1)])
+        assert L.apd_set_cameras(h, C.c_void_p(cams.ctypes.data)) == 0
+        cams[:] = 0                                   # the engine keeps its own copy of the (small) camera array
+        assert L.apd_set_priors(h, vp(pl), vp(vw), vp(st)) == 0
+        assert L.apd_set_images(h, ptrs(imgs), W * 4) == 0
+        assert L.apd_set_depths(h, ptrs(deps), W * 4) == 0
+        assert L.apd_run(h) == 0
+        planes = np.empty((H, W, 4), np.float32); states = np.empty((H, W), np.uint8); views = np.empty((H, W), np.uint32)
+        assert L.apd_get_planes(h, C.c_void_p(planes.ctypes.data)) == 0
+        assert L.apd_get_states(h, C.c_void_p(states.ctypes.data)) == 0 and L.apd_get_views(h, C.c_void_p(views.ctypes.data)) == 0
+        assert np.array_equal(bits(planes.reshape(ref["planes"].shape)), bits(ref["planes"]))
+        assert np.array_equal(states.reshape(ref["states"].shape), ref["states"]) and np.array_equal(views.reshape(ref["views"].shape), ref["views"])
+    assert L.apd_set_upload_mode(h, 0) == 0
+    L.apd_destroy(h)
