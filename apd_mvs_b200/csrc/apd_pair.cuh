@@ -174,4 +174,50 @@ __device__ __forceinline__ void wq_cache_window(const Args &a, int cx, int cy, f
 }
 
 
+// ComputeGeomConsistencyCost's view-dependent half (geom_cost_at, apd_device.cuh) for the two slots: world point P0
+// against source view va, P1 against vb. Negations sit on an operand ((-x)*y == -(x*y) exactly); subtractions are additions of
+// the negated operand.
+__device__ __forceinline__ void geom_cost_at2(const Args &a, const RefConst &rc, const ViewConst &va, const ViewConst &vb, int la, int lb,
+                                              const GeomPoint P0, const GeomPoint P1, float xf, float yf, float &g0, float &g1) {
+	const apd_camera &s0 = va.cam, &s1 = vb.cam;
+#define PK(f) pk2(s0.f, s1.f)
+	const f32x2 Px = pk2(P0.x, P1.x), Py = pk2(P0.y, P1.y), Pz = pk2(P0.z, P1.z);
+	const f32x2 tx = add2(PK(t[0]), fma2(PK(R[2]), Pz, fma2(PK(R[0]), Px, mul2(PK(R[1]), Py))));
+	const f32x2 ty = add2(PK(t[1]), fma2(PK(R[5]), Pz, fma2(PK(R[3]), Px, mul2(PK(R[4]), Py))));
+	const f32x2 tz = add2(PK(t[2]), fma2(PK(R[8]), Pz, fma2(PK(R[6]), Px, mul2(PK(R[7]), Py))));
+	float d0, d1;
+	unpk2(fma2(PK(K[8]), tz, fma2(PK(K[6]), tx, mul2(PK(K[7]), ty))), d0, d1);
+	const f32x2 rd = pk2(rcpf(d0), rcpf(d1));
+	const f32x2 SX = mul2(fma2(PK(K[2]), tz, fma2(PK(K[0]), tx, mul2(PK(K[1]), ty))), rd);
+	const f32x2 SY = mul2(fma2(PK(K[5]), tz, fma2(PK(K[3]), tx, mul2(PK(K[4]), ty))), rd);
+	float sx0, sx1, sy0, sy1;
+	unpk2(SX, sx0, sx1); unpk2(SY, sy0, sy1);
+	const float sd0 = tex2DLayered<float>(a.depth_tex, (float)(int)sx0 + 0.5f, (float)(int)sy0 + 0.5f, la);
+	const float sd1 = tex2DLayered<float>(a.depth_tex, (float)(int)sx1 + 0.5f, (float)(int)sy1 + 0.5f, lb);
+	const f32x2 SD = pk2(sd0, sd1);
+	const f32x2 rsK0 = pk2(rcpf(s0.K[0]), rcpf(s1.K[0])), rsK4 = pk2(rcpf(s0.K[4]), rcpf(s1.K[4]));
+	const f32x2 Y0 = mul2(mul2(SD, add2(SX, pk2(-s0.K[2], -s1.K[2]))), rsK0);
+	const f32x2 Y1 = mul2(mul2(SD, add2(SY, pk2(-s0.K[5], -s1.K[5]))), rsK4);
+	const f32x2 Qx = add2(PK(c[0]), fma2(PK(R[6]), SD, fma2(PK(R[0]), Y0, mul2(PK(R[3]), Y1))));
+	const f32x2 Qy = add2(PK(c[1]), fma2(PK(R[7]), SD, fma2(PK(R[1]), Y0, mul2(PK(R[4]), Y1))));
+	const f32x2 Qz = add2(PK(c[2]), fma2(PK(R[8]), SD, fma2(PK(R[2]), Y0, mul2(PK(R[5]), Y1))));
+#undef PK
+	const float *R = rc.cam.R; const float *K = rc.cam.K; const float *t = rc.cam.t;
+#define BC(x) pk2(x, x)
+	const f32x2 ux = add2(BC(t[0]), fma2(BC(R[2]), Qz, fma2(BC(R[0]), Qx, mul2(BC(R[1]), Qy))));
+	const f32x2 uy = add2(BC(t[1]), fma2(BC(R[5]), Qz, fma2(BC(R[3]), Qx, mul2(BC(R[4]), Qy))));
+	const f32x2 uz = add2(BC(t[2]), fma2(BC(R[8]), Qz, fma2(BC(R[6]), Qx, mul2(BC(R[7]), Qy))));
+	float b0, b1;
+	unpk2(fma2(BC(K[8]), uz, fma2(BC(K[6]), ux, mul2(BC(K[7]), uy))), b0, b1);
+	const f32x2 nrb = pk2(-rcpf(b0), -rcpf(b1));
+	const f32x2 DC = fma2(fma2(BC(K[2]), uz, fma2(BC(K[0]), ux, mul2(BC(K[1]), uy))), nrb, BC(xf));
+	const f32x2 DR = fma2(fma2(BC(K[5]), uz, fma2(BC(K[3]), ux, mul2(BC(K[4]), uy))), nrb, BC(yf));
+#undef BC
+	float e0, e1;
+	unpk2(fma2(DC, DC, mul2(DR, DR)), e0, e1);
+	g0 = (sd0 == 0.0f) ? 3.0f : fminf(sqrtaf(e0), 3.0f);
+	g1 = (sd1 == 0.0f) ? 3.0f : fminf(sqrtaf(e1), 3.0f);
+}
+
+
 }  // namespace apd
