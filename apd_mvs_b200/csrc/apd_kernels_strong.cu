@@ -6,7 +6,8 @@
 //   k_strong           K6/K7 Black/RedPixelUpdateStrong APD.cu:1547-1585 -> :982-1321 -> :837-890
 //   k_depth_normal     K11 GetDepthandNormal          APD.cu:1587-1602
 //   k_median           K12/K13 Black/RedPixelFilterStrong APD.cu:1604-1748
-//   k_sweep            K14 DepthToWeak + K15 LocalRefine (fused)  APD.cu:1990-2144, 2146-2232
+//   k_sweep            K14 DepthToWeak + K15 LocalRefine (fused)  APD.cu:1990-2144, 2146-2232 -- FIRST design, selectable with
+//                      APD_SWEEP_IMPL=old for A/B timing; the shipped depth sweep is k_sweep_q (apd_kernels_sweepq.cu)
 // Design (not a translation):
 //   * every NCC evaluation is fetched by the four lanes of a quad (each takes a 3x3 quadrant of the 6x6 window, so a
 //     texture instruction covers 2x2 clusters of neighbouring taps), staged through a per-warp shared-memory slab, and
