@@ -1,6 +1,7 @@
 // Host-side stand-in for <boost/filesystem.hpp>, enough for the unmodified reference APD.cpp. Test infrastructure only.
 #ifndef APD_ORACLE_SHIM_HOST_BOOST_FS_HPP
 #define APD_ORACLE_SHIM_HOST_BOOST_FS_HPP
+#include <cstdlib>
 #include <fstream>
 #include <ostream>
 #include <string>
@@ -30,6 +31,8 @@ public:
 };
 inline bool exists(const path &p) { struct stat st; return stat(p.string().c_str(), &st) == 0; }
 inline bool create_directory(const path &p) { return mkdir(p.string().c_str(), 0777) == 0; }
-inline bool remove(const path &p) { return unlink(p.string().c_str()) == 0; }
+// APD_SHIM_KEEP_FILES=1 (tests only): main()'s clean-up of the intermediate .dmb / .bin files (main.cpp:219-226) becomes a no-op, so a
+// test can read what the reference program wrote
+inline bool remove(const path &p) { if (getenv("APD_SHIM_KEEP_FILES")) return true; return unlink(p.string().c_str()) == 0; }
 }}  // namespace boost::filesystem
 #endif
