@@ -179,16 +179,18 @@ extern "C" int apd_set_params(apd_handle h, const apd_params *p) {
 }
 extern "C" int apd_set_seed(apd_handle h, uint64_t seed) { if (!h) return APD_E_ARG; h->seed = seed; return APD_OK; }
 
+static void drain_uploads(apd_handle h);
 extern "C" int apd_set_num_images(apd_handle h, int num_images) {
 	if (!h) return APD_E_ARG;
 	if (num_images < 2 || num_images > h->capacity) return fail(h, APD_E_LIMIT, "num_images must be 2..the count given to apd_create");
-	if (num_images != h->N) { h->have_images = h->have_cams = h->have_depths = false; }
+	if (num_images != h->N) { drain_uploads(h); h->have_images = h->have_cams = h->have_depths = false; }
 	h->N = num_images; h->S = num_images - 1; h->params.num_images = num_images;
 	return APD_OK;
 }
 
 extern "C" int apd_reset_inputs(apd_handle h) {
 	if (!h) return APD_E_ARG;
+	drain_uploads(h);
 	h->have_images = h->have_cams = h->have_depths = h->have_planes = h->have_states = false;
 	return APD_OK;
 }
@@ -211,6 +213,12 @@ static int finish_upload(apd_handle h, bool host, bool late) {
 	}
 	CKH(cudaStreamSynchronize(h->stream));
 	return APD_OK;
+}
+
+// Asynchronous uploads still in flight are completed before anything that ends their contract early (inputs forgotten, a run refused):
+// the caller may release its host buffers as soon as such a call returns.
+static void drain_uploads(apd_handle h) {
+	if (h->pending_early || h->pending_late) { cudaStreamSynchronize(h->copy_stream); h->pending_early = h->pending_late = false; }
 }
 
 extern "C" int apd_set_cameras(apd_handle h, const apd_camera *cams) {
@@ -334,10 +342,12 @@ static Args make_args(apd_handle h) {
 extern "C" int apd_run_until(apd_handle h, int stage_end) {
 	if (!h) return APD_E_ARG;
 	const apd_params &p = h->params;
-	if (!h->have_images || !h->have_cams) return fail(h, APD_E_STATE, "set cameras and images first");
-	if (p.geom_consistency && !h->have_depths) return fail(h, APD_E_STATE, "geom_consistency needs apd_set_depths (APD.cpp:492-510)");
-	if (p.state != APD_FIRST_INIT && !h->have_planes) return fail(h, APD_E_STATE, "state != FIRST_INIT needs prior planes+views (APD.cpp:552-581)");
-	if (p.use_APD && !h->have_states) return fail(h, APD_E_STATE, "use_APD needs prior pixel states (APD.cpp:513-519)");
+	const char *missing = nullptr;
+	if (!h->have_images || !h->have_cams) missing = "set cameras and images first";
+	else if (p.geom_consistency && !h->have_depths) missing = "geom_consistency needs apd_set_depths (APD.cpp:492-510)";
+	else if (p.state != APD_FIRST_INIT && !h->have_planes) missing = "state != FIRST_INIT needs prior planes+views (APD.cpp:552-581)";
+	else if (p.use_APD && !h->have_states) missing = "use_APD needs prior pixel states (APD.cpp:513-519)";
+	if (missing) { drain_uploads(h); return fail(h, APD_E_STATE, missing); }
 	CKH(cudaSetDevice(h->device));
 	const int nstages = apd_num_stages(h);
 	if (stage_end < 0 || stage_end >= nstages) stage_end = nstages - 1;
