@@ -14,4 +14,4 @@ for k in o['roofline']['kernels']: print(k['kernel'], k['frac'], k.get('tex',{})
 print(o['secondary']['cfg2']['iter_ms'], r['secondary']['cfg2']['iter_ms'], o['secondary']['cfg2'].get('ms_per_step'), r['secondary']['cfg2'].get('ms_per_step'), o['secondary']['cfg4']['wall_ms'])
 print(o['stage_ms']); print(r['stage_ms'])
 PY
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02e_cfg3_launches.csv python tests/tools/time_ours.py cfg3 1 launches > /dev/null 2>&1; wc -l gpurun_out/r02d_cfg3_launches.csv
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_' -c 200 --csv --log-file gpurun_out/r02e_cfg3_launches.csv python tests/tools/time_ours.py cfg3 1 launches > /dev/null 2>&1; wc -l gpurun_out/r02d_cfg3_launches.csv
